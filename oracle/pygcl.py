@@ -1,0 +1,154 @@
+"""Restatement of the PyGCL 0.1.2 objects the GCL path constructs.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Call sites: gcl_module.py:127 (SingleBranchContrast(JSD, "G2L")), :142 (its
+call), :171-173 (DualBranchContrast(InfoNCE(0.2), "L2L", intraview_negs=True)),
+:189 (its call).  Semantics: SURVEY.md Appendix A.4 / A.5.  Each loss exists
+twice - the mask-materialising form PyGCL executes ("as written") and the
+closed form the CUDA kernels implement - and tests/test_oracle.py checks
+they agree.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------
+# InfoNCE / DualBranchContrast (GRACE)
+# --------------------------------------------------------------------------
+def _similarity(h1: torch.Tensor, h2: torch.Tensor) -> torch.Tensor:
+    # GCL.losses.infonce._similarity: F.normalize (p=2, dim=1, eps=1e-12) then h1 @ h2.T
+    return F.normalize(h1) @ F.normalize(h2).t()
+
+
+def _infonce_compute(anchor, sample, pos_mask, neg_mask, tau: float):
+    # GCL.losses.InfoNCE.compute - no max-subtraction, masks multiply exp(sim)
+    sim = _similarity(anchor, sample) / tau
+    exp_sim = torch.exp(sim) * (pos_mask + neg_mask)
+    log_prob = sim - torch.log(exp_sim.sum(dim=1, keepdim=True))
+    loss = log_prob * pos_mask
+    loss = loss.sum(dim=1) / pos_mask.sum(dim=1)
+    return -loss.mean()
+
+
+def _same_scale_sampler(anchor, sample, intraview_negs: bool):
+    # GCL.models.samplers.SameScaleSampler + add_intraview_negs
+    n = anchor.size(0)
+    pos = torch.eye(n, dtype=anchor.dtype, device=anchor.device)
+    neg = 1.0 - pos
+    if intraview_negs:
+        sample = torch.cat([sample, anchor], dim=0)
+        pos = torch.cat([pos, torch.zeros_like(pos)], dim=1)
+        neg = torch.cat([neg, 1.0 - torch.eye(n, dtype=anchor.dtype, device=anchor.device)], dim=1)
+    return anchor, sample, pos, neg
+
+
+def infonce_l2l_as_written(h1: torch.Tensor, h2: torch.Tensor, tau: float = 0.2, intraview_negs: bool = True):
+    """DualBranchContrast.forward(h1, h2) in mode "L2L": materialises the
+    [N, 2N] similarity / exp / mask tensors exactly as PyGCL does."""
+    a1, s1, p1, n1 = _same_scale_sampler(h1, h2, intraview_negs)
+    a2, s2, p2, n2 = _same_scale_sampler(h2, h1, intraview_negs)
+    l1 = _infonce_compute(a1, s1, p1, n1, tau)
+    l2 = _infonce_compute(a2, s2, p2, n2, tau)
+    return (l1 + l2) * 0.5
+
+
+def infonce_l2l_closed_form(h1: torch.Tensor, h2: torch.Tensor, tau: float = 0.2):
+    """Closed form: with a = normalize(h1), b = normalize(h2),
+    r1_i = sum_j exp(S12_ij) + sum_{j != i} exp(S11_ij), r2_i likewise with S12^T, S22;
+    loss = -(1/2N) sum_i [ 2 S12_ii - log r1_i - log r2_i ]."""
+    a, b = F.normalize(h1), F.normalize(h2)
+    s12 = a @ b.t() / tau
+    s11 = a @ a.t() / tau
+    s22 = b @ b.t() / tau
+    n = a.size(0)
+    off = 1.0 - torch.eye(n, dtype=a.dtype)
+    r1 = torch.exp(s12).sum(1) + (torch.exp(s11) * off).sum(1)
+    r2 = torch.exp(s12).sum(0) + (torch.exp(s22) * off).sum(1)
+    d = torch.diagonal(s12)
+    return -(2.0 * d - torch.log(r1) - torch.log(r2)).sum() / (2.0 * n)
+
+
+class DualBranchContrast(torch.nn.Module):
+    """Oracle stand-in for GCL.models.DualBranchContrast (L2L only, as used)."""
+
+    def __init__(self, loss, mode: str = "L2L", intraview_negs: bool = False, **kwargs):
+        super().__init__()
+        assert mode == "L2L", "the GCL path only constructs mode='L2L' (gcl_module.py:171-173)"
+        self.loss, self.mode, self.intraview_negs = loss, mode, intraview_negs
+
+    def forward(self, h1=None, h2=None, **kw):
+        return infonce_l2l_as_written(h1, h2, self.loss.tau, self.intraview_negs)
+
+
+class InfoNCE:
+    def __init__(self, tau):
+        self.tau = tau
+
+
+# --------------------------------------------------------------------------
+# JSD / SingleBranchContrast (DGI)
+# --------------------------------------------------------------------------
+def jsd_g2l_as_written(h: torch.Tensor, g: torch.Tensor, hn: torch.Tensor):
+    """SingleBranchContrast(JSD(), "G2L").forward(h=z, g=g, hn=zn), batch=None.
+    CrossScaleSampler: anchor=g [1,D], sample=cat(h,hn) [2N,D], pos=[1_N|0_N]."""
+    n = h.size(0)
+    sample = torch.cat([h, hn], dim=0)
+    pos = torch.cat([torch.ones(1, n, dtype=h.dtype), torch.zeros(1, n, dtype=h.dtype)], dim=1)
+    neg = 1.0 - pos
+    sim = g @ sample.t()
+    # GCL.losses.JSD.compute
+    num_pos = pos.int().sum()
+    num_neg = neg.int().sum()
+    e_pos = (math.log(2.0) - F.softplus(-sim * pos)).sum() / num_pos
+    neg_sim = sim * neg
+    e_neg = (F.softplus(-neg_sim) + neg_sim - math.log(2.0)).sum() / num_neg
+    return e_neg - e_pos
+
+
+def jsd_g2l_closed_form(h: torch.Tensor, g: torch.Tensor, hn: torch.Tensor):
+    """mean softplus(-s+) + mean softplus(s-) - 2 ln2, s+ = h g^T, s- = hn g^T."""
+    sp = (h @ g.t()).squeeze(-1)
+    sn = (hn @ g.t()).squeeze(-1)
+    return F.softplus(-sp).mean() + F.softplus(sn).mean() - 2.0 * math.log(2.0)
+
+
+class SingleBranchContrast(torch.nn.Module):
+    """Oracle stand-in for GCL.models.SingleBranchContrast (G2L only, as used)."""
+
+    def __init__(self, loss, mode: str = "G2L", **kwargs):
+        super().__init__()
+        assert mode == "G2L", "the GCL path only constructs mode='G2L' (gcl_module.py:127)"
+        self.loss, self.mode = loss, mode
+
+    def forward(self, h=None, g=None, batch=None, hn=None, **kw):
+        assert batch is None
+        return jsd_g2l_as_written(h, g, hn)
+
+
+class JSD:
+    pass
+
+
+# --------------------------------------------------------------------------
+# GGD head + BCE (model/gcl.py:83-91, gcl_module.py:229-234)
+# --------------------------------------------------------------------------
+def ggd_loss_as_written(pos_z, neg_z, weight, bias):
+    pos_h = (pos_z @ weight.t() + bias).sum(1)
+    neg_h = (neg_z @ weight.t() + bias).sum(1)
+    pred = torch.cat([pos_h, neg_h])
+    gt = torch.cat([torch.ones_like(pos_h), torch.zeros_like(neg_h)])
+    return F.binary_cross_entropy_with_logits(pred, gt)
+
+
+def ggd_loss_closed_form(pos_z, neg_z, weight, bias):
+    """(z W^T + b).sum(1) == z . (sum_rows W) + sum(b); BCE(1/0) == softplus sums."""
+    wv = weight.sum(0)
+    bs = bias.sum()
+    sp = pos_z @ wv + bs
+    sn = neg_z @ wv + bs
+    return (F.softplus(-sp).sum() + F.softplus(sn).sum()) / (2 * pos_z.size(0))
