@@ -1,0 +1,280 @@
+// Streaming elementwise / small-reduction kernels around the GCL step.
+//   - mask_feature (model/gcl.py:40-41,75) fused with the fp32 -> bf16 cast of x
+//   - ReLU+dropout backward (encoder.py:155-158) fused with the bias gradient
+//   - modality mean (gcl_module.py:47-48)
+//   - L2 row normalisation (PyGCL InfoNCE _similarity) + its backward
+//   - deterministic column sums (two-stage, fixed order, no atomics)
+// All HBM-bound, 128-bit vectorised, grid sized in multiples of the SM count.
+#include "common.cuh"
+#include "../../include/bmkg_b200.h"
+
+namespace bmkg {
+
+constexpr int kEwThreads = 256;
+inline unsigned ew_grid(int64_t work_items) {
+  int64_t g = ceil_div(work_items, kEwThreads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// x fp32 [n] (n % 4 == 0) -> up to three bf16 copies: plain, masked by keep1, masked by keep2
+__global__ void __launch_bounds__(kEwThreads) mask_cast_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep1,
+                                                               const uint8_t* __restrict__ keep2, int64_t n4,
+                                                               __nv_bfloat16* __restrict__ x0, __nv_bfloat16* __restrict__ x1,
+                                                               __nv_bfloat16* __restrict__ x2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (x0) reinterpret_cast<uint2*>(x0)[i] = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    if (x1) {
+      const uint32_t m = reinterpret_cast<const uint32_t*>(keep1)[i];
+      reinterpret_cast<uint2*>(x1)[i] = make_uint2(pack2((m & 0xffu) ? v.x : 0.f, (m & 0xff00u) ? v.y : 0.f),
+                                                   pack2((m & 0xff0000u) ? v.z : 0.f, (m & 0xff000000u) ? v.w : 0.f));
+    }
+    if (x2) {
+      const uint32_t m = reinterpret_cast<const uint32_t*>(keep2)[i];
+      reinterpret_cast<uint2*>(x2)[i] = make_uint2(pack2((m & 0xffu) ? v.x : 0.f, (m & 0xff00u) ? v.y : 0.f),
+                                                   pack2((m & 0xff0000u) ? v.z : 0.f, (m & 0xff000000u) ? v.w : 0.f));
+    }
+  }
+}
+
+// mean over the modality axis: x fp32 [N, M, F] -> fp32 / bf16 [N, F]
+__global__ void __launch_bounds__(kEwThreads) modality_mean_kernel(const float* __restrict__ x, int64_t N, int M, int F4,
+                                                                   float* __restrict__ out_f32,
+                                                                   __nv_bfloat16* __restrict__ out_bf16) {
+  const int64_t total = N * F4;
+  const float inv = 1.0f / (float)M;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / F4, f = i % F4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < M; ++m) {
+      const float4 v = reinterpret_cast<const float4*>(x)[(n * M + m) * F4 + f];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[i] = a;
+    if (out_bf16) reinterpret_cast<uint2*>(out_bf16)[i] = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+  }
+}
+
+// g_pre = (y > 0) ? g_y * scale : 0   (y = dropout(relu(pre)) so y > 0 <=> kept and pre > 0)
+// and per-CTA column partial sums of g_pre for the bias gradient.
+// grid.x CTAs each own a contiguous row range; thread t owns column-octet t % (C/8).
+__global__ void __launch_bounds__(kEwThreads) relu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                                      const __nv_bfloat16* __restrict__ y, float scale,
+                                                                      int64_t N, int C, int rows_per_cta,
+                                                                      __nv_bfloat16* __restrict__ gpre,
+                                                                      float* __restrict__ partial /*[grid, C]*/) {
+  extern __shared__ float red[];  // [groups][C]
+  const int oct = C / 8;
+  const int groups = kEwThreads / oct;  // row groups per CTA iteration (host guarantees >= 1)
+  const int g = threadIdx.x / oct, o = threadIdx.x % oct;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(N, r0 + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < groups) {
+    for (int64_t r = r0 + g; r < r1; r += groups) {
+      const uint4 ug = ldg_stream(gy + r * C + o * 8);
+      const uint4 uy = ldg_stream(y + r * C + o * 8);
+      float fg[8], fy[8], res[8];
+      unpack8(ug, fg);
+      unpack8(uy, fy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = fy[i] > 0.f ? fg[i] * scale : 0.f;
+      }
+      const uint4 packed = pack8(res);
+      *reinterpret_cast<uint4*>(gpre + r * C + o * 8) = packed;
+      float rb[8];
+      unpack8(packed, rb);  // sum what downstream actually sees (bf16-rounded)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += rb[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[g * C + o * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += red[gg * C + c];
+    partial[(int64_t)blockIdx.x * C + c] = s;
+  }
+}
+
+// out[c] = sum_b partial[b, c] in fixed order
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * C + c];
+  out[c] = s;
+}
+
+// column partial sums of a fp32 [N, C] matrix (optionally row-weighted), same CTA/row layout
+__global__ void __launch_bounds__(kEwThreads) colsum_partial_kernel(const float* __restrict__ z, const float* __restrict__ roww,
+                                                                    int64_t N, int C, int rows_per_cta,
+                                                                    float* __restrict__ partial) {
+  extern __shared__ float red[];
+  const int quad = C / 4;
+  const int groups = kEwThreads / quad;
+  const int g = threadIdx.x / quad, o = threadIdx.x % quad;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(N, r0 + rows_per_cta);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g < groups) {
+    for (int64_t r = r0 + g; r < r1; r += groups) {
+      const float4 v = reinterpret_cast<const float4*>(z + r * C)[o];
+      const float w = roww ? roww[r] : 1.f;
+      acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    }
+    reinterpret_cast<float4*>(red + g * C)[o] = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += red[gg * C + c];
+    partial[(int64_t)blockIdx.x * C + c] = s;
+  }
+}
+
+// one warp per row: z = bf16( h / max(|h|, eps) * scale ), inv_norm = 1 / max(|h|, eps)
+__global__ void __launch_bounds__(256) l2norm_scale_kernel(const float* __restrict__ h, int64_t N, int D, float scale,
+                                                           __nv_bfloat16* __restrict__ z, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* hp = h + row * D;
+  float ss = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) inv_norm[row] = inv;
+  const float s = inv * scale;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + c);
+    *reinterpret_cast<uint2*>(z + row * D + c) = make_uint2(pack2(v.x * s, v.y * s), pack2(v.z * s, v.w * s));
+  }
+}
+
+// dh = scale * inv * (dz - u (u . dz)),  u = h * inv   (straight-through the bf16 rounding)
+__global__ void __launch_bounds__(256) l2norm_scale_bwd_kernel(const float* __restrict__ h, const float* __restrict__ inv_norm,
+                                                               const float* __restrict__ dz, int64_t N, int D, float scale,
+                                                               float* __restrict__ dh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float inv = inv_norm[row];
+  const float* hp = h + row * D;
+  const float* gp = dz + row * D;
+  float dot = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + c);
+    const float4 g = *reinterpret_cast<const float4*>(gp + c);
+    dot += v.x * g.x + v.y * g.y + v.z * g.z + v.w * g.w;
+  }
+  dot = warp_sum(dot) * inv;  // u . dz
+  const float s = scale * inv;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(hp + c);
+    const float4 g = *reinterpret_cast<const float4*>(gp + c);
+    float4 o;
+    o.x = s * (g.x - v.x * inv * dot);
+    o.y = s * (g.y - v.y * inv * dot);
+    o.z = s * (g.z - v.z * inv * dot);
+    o.w = s * (g.w - v.w * inv * dot);
+    *reinterpret_cast<float4*>(dh + row * D + c) = o;
+  }
+}
+
+inline int colsum_ctas(int64_t N) {
+  int64_t b = ceil_div(N, 64);
+  const int64_t cap = kNumSMs * 4;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace bmkg
+
+using namespace bmkg;
+
+extern "C" {
+
+int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, int64_t n, void* x0, void* x1, void* x2,
+                   void* stream) {
+  BMKG_REQUIRE(x && n >= 0 && n % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE((!x1 || keep1) && (!x2 || keep2), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(x), BMKG_ERR_MISALIGNED);
+  if (n == 0) return BMKG_OK;
+  mask_cast_kernel<<<ew_grid(n / 4), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, keep1, keep2, n / 4, static_cast<__nv_bfloat16*>(x0), static_cast<__nv_bfloat16*>(x1),
+      static_cast<__nv_bfloat16*>(x2));
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_modality_mean(const float* x, int64_t N, int M, int F, float* out_f32, void* out_bf16, void* stream) {
+  BMKG_REQUIRE(x && N > 0 && M > 0 && F > 0 && F % 4 == 0 && (out_f32 || out_bf16), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(x), BMKG_ERR_MISALIGNED);
+  modality_mean_kernel<<<ew_grid(N * (F / 4)), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, N, M, F / 4, out_f32, static_cast<__nv_bfloat16*>(out_bf16));
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+size_t bmkg_colsum_workspace_bytes(int64_t N, int C) { return (size_t)colsum_ctas(N) * C * sizeof(float); }
+
+int bmkg_relu_dropout_bwd(const void* gy_bf16, const void* y_bf16, float scale, int64_t N, int C, void* gpre_bf16, float* dbias,
+                          void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(gy_bf16 && y_bf16 && gpre_bf16 && dbias && N > 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(C % 8 == 0 && C >= 8 && C / 8 <= kEwThreads, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_colsum_workspace_bytes(N, C), BMKG_ERR_WORKSPACE);
+  BMKG_REQUIRE(aligned16(gy_bf16) && aligned16(y_bf16) && aligned16(gpre_bf16), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = colsum_ctas(N);
+  const int rows_per_cta = (int)ceil_div(N, nb);
+  const int groups = kEwThreads / (C / 8);
+  relu_dropout_bwd_kernel<<<nb, kEwThreads, (size_t)groups * C * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(gy_bf16), static_cast<const __nv_bfloat16*>(y_bf16), scale, N, C, rows_per_cta,
+      static_cast<__nv_bfloat16*>(gpre_bf16), static_cast<float*>(ws));
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), nb, C, dbias);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_colsum(const float* z, const float* row_weight, int64_t N, int C, float* out, void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(z && out && N > 0 && C % 4 == 0 && C >= 4 && C / 4 <= kEwThreads, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_colsum_workspace_bytes(N, C), BMKG_ERR_WORKSPACE);
+  BMKG_REQUIRE(aligned16(z), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = colsum_ctas(N);
+  const int rows_per_cta = (int)ceil_div(N, nb);
+  const int groups = kEwThreads / (C / 4);
+  colsum_partial_kernel<<<nb, kEwThreads, (size_t)groups * C * sizeof(float), st>>>(z, row_weight, N, C, rows_per_cta,
+                                                                                    static_cast<float*>(ws));
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), nb, C, out);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_l2norm_scale(const float* h, int64_t N, int D, float scale, void* z_bf16, float* inv_norm, void* stream) {
+  BMKG_REQUIRE(h && z_bf16 && inv_norm && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(h) && aligned16(z_bf16), BMKG_ERR_MISALIGNED);
+  l2norm_scale_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h, N, D, scale, static_cast<__nv_bfloat16*>(z_bf16), inv_norm);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_l2norm_scale_bwd(const float* h, const float* inv_norm, const float* dz, int64_t N, int D, float scale, float* dh,
+                          void* stream) {
+  BMKG_REQUIRE(h && inv_norm && dz && dh && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(h) && aligned16(dz) && aligned16(dh), BMKG_ERR_MISALIGNED);
+  l2norm_scale_bwd_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, inv_norm, dz, N, D,
+                                                                                                  scale, dh);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+}  // extern "C"

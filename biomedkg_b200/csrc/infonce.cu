@@ -1,0 +1,575 @@
+// I1/I2 - fused GRACE InfoNCE on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces PyGCL DualBranchContrast(InfoNCE(tau=0.2), "L2L", intraview_negs=True)
+// as constructed at biomedkg/gcl_module.py:171-173 and called at :189.  PyGCL
+// materialises ~7 [N,2N] fp32 tensors per direction; here the
+// similarity matrix never leaves the SM.
+//
+// Formulation.  Stack the two normalised views Z = [a; b] (2N x D, bf16,
+// pre-scaled by sqrt(log2(e)/tau) so that z_u . z_v is the logit in log2
+// units).  The three similarity blocks S11, S12, S22 are the blocks of the
+// Gram matrix Z Z^T and both InfoNCE denominators are its off-diagonal row sums
+//      R_u = sum_{v != u} 2^(z_u . z_v)
+//      loss = (1/2N) [ sum_u ln R_u - 2 ln2 sum_i z_i . z_{N+i} ].
+// |logit| <= 1/tau so a fixed shift replaces the online max: no rescale pass.
+//
+// Forward: persistent CTAs; each owns a 128-row block of Z (A operand, resident
+// in smem) and streams 128-row column tiles of Z (B operand) through a TMA +
+// mbarrier ring; tcgen05.mma (M=128,N=128,K=16, bf16 -> fp32) writes S tiles into
+// a 4-deep ring of TMEM accumulators; two softmax warpgroups pull tiles with
+// tcgen05.ld, apply ex2, mask the diagonal and keep per-row partial sums in
+// registers.  Backward: same stream; P = 2^S (1/R_u + 1/R_v) is written back to
+// TMEM as bf16 (aliasing S) and a second tcgen05.mma with A from TMEM and the
+// same smem tile as an MN-major B accumulates dZ_u = sum_v P_uv z_v in TMEM.
+//
+// Tensor-bound.  Algorithmic FLOPs: fwd 6 N^2 D, bwd 8 N^2 D.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/bmkg_b200.h"
+
+namespace bmkg {
+namespace nce {
+
+constexpr int kBM = 128;             // rows of Z per CTA work item (UMMA M)
+constexpr int kBN = 128;             // rows of Z per streamed column tile (UMMA N)
+constexpr int kPanelElems = 64;      // 64 bf16 = 128 B = one swizzle row
+constexpr int kPanelBytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kMaxPanels = 4;        // D <= 256
+constexpr int kStages = 2;
+constexpr int kAccBufs = 4;          // fwd: 4 x 128 TMEM columns
+constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2-9 softmax (2 warpgroups)
+constexpr int kTmemCols = 512;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kPanelBytes * kMaxPanels * (1 + kStages) + 256 /*barriers*/;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Schedule {
+  int nrb, ntiles, nchunks, tiles_per_chunk;
+};
+
+// ----------------------------------------------------------------------------
+// forward
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int npanels, Schedule sch, int rows_padded,
+                   float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kPanelBytes * kMaxPanels;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPanelBytes * kMaxPanels * (1 + kStages));
+  uint64_t* full = bars;                  // [kStages]
+  uint64_t* empty = bars + kStages;       // [kStages]
+  uint64_t* a_full = bars + 2 * kStages;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* tfull = a_empty + 1;          // [kAccBufs]
+  uint64_t* tempty = tfull + kAccBufs;    // [kAccBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccBufs);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    for (int b = 0; b < kAccBufs; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmap);
+  }
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = sch.nrb * sch.nchunks;
+  const uint32_t tile_bytes = (uint32_t)npanels * kPanelBytes;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t sphase = 0, aphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = item / sch.nchunks, cc = item % sch.nchunks;
+        ptx::mbar_wait(a_empty, aphase ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
+        for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPanelBytes, &tmap, a_full, p * kPanelElems, rb * kBM);
+        aphase ^= 1;
+        const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
+        for (int ct = t0; ct < t1; ++ct) {
+          ptx::mbar_wait(&empty[stage], sphase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          uint8_t* dst = sB + (size_t)stage * kPanelBytes * kMaxPanels;
+          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          if (++stage == kStages) { stage = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t sphase = 0, accphase = 0, aphase = 0;
+      const uint32_t a_addr = ptx::smem_u32(sA);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cc = item % sch.nchunks;
+        ptx::mbar_wait(a_full, aphase);
+        aphase ^= 1;
+        const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
+        for (int ct = t0; ct < t1; ++ct) {
+          ptx::mbar_wait(&tempty[acc], accphase ^ 1);
+          ptx::mbar_wait(&full[stage], sphase);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(sB + (size_t)stage * kPanelBytes * kMaxPanels);
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBN;
+          const int ksteps = npanels * 4;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t off = (uint32_t)(kk >> 2) * kPanelBytes + (uint32_t)(kk & 3) * 32u;
+            ptx::umma_ss(d_tmem, ptx::smem_desc_sw128(a_addr + off, 16, 1024), ptx::smem_desc_sw128(b_addr + off, 16, 1024),
+                         idesc, kk > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);
+          ptx::umma_commit(&tfull[acc]);
+          if (++stage == kStages) { stage = 0; sphase ^= 1; }
+          if (++acc == kAccBufs) { acc = 0; accphase ^= 1; }
+        }
+        ptx::umma_commit(a_empty);
+      }
+    }
+  } else {  // ---------------- softmax warpgroups ----------------
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int lrow = quarter * 32 + lane;
+    int tcount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rb = item / sch.nchunks, cc = item % sch.nchunks;
+      const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int ct = t0; ct < t1; ++ct, ++tcount) {
+        if ((tcount & 1) != wg) continue;
+        const int acc = tcount & (kAccBufs - 1);
+        const uint32_t ph = (uint32_t)(tcount / kAccBufs) & 1u;
+        ptx::mbar_wait(&tfull[acc], ph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+        const bool diag = (ct == rb);
+#pragma unroll
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (c == kBN / 32 - 1) {  // accumulator fully in registers: hand the buffer back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          }
+          if (diag) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j == lrow) r[j] = 0xff800000u;  // -inf -> ex2 = 0
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            s0 += ex2(__uint_as_float(r[j]));
+            s1 += ex2(__uint_as_float(r[j + 1]));
+            s2 += ex2(__uint_as_float(r[j + 2]));
+            s3 += ex2(__uint_as_float(r[j + 3]));
+          }
+        }
+      }
+      const int row = rb * kBM + lrow;
+      if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s0 + s1) + (s2 + s3);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// R_u, 1/R_u, ln R_u and the positive-pair logits; fixed-order block partials.
+__global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
+                                                                    int rows, int N, int D, float npad,
+                                                                    const __nv_bfloat16* __restrict__ z,
+                                                                    float* __restrict__ inv_r, float* __restrict__ block_part) {
+  __shared__ float red[8];
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (u < rows) {
+    float R = 0.f;
+    for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
+    R -= npad;
+    inv_r[u] = 1.0f / R;
+    term = logf(R);
+    if (u < N) {
+      const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
+      const uint4* zb = reinterpret_cast<const uint4*>(z + (size_t)(u + N) * D);
+      float dot = 0.f;
+      for (int c = 0; c < D / 8; ++c) {
+        float fa[8], fb[8];
+        unpack8(za[c], fa);
+        unpack8(zb[c], fb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(fa[i], fb[i], dot);
+      }
+      term -= 2.0f * 0.6931471805599453f * dot;
+    }
+  } else if (u < rows_padded) {
+    inv_r[u] = 0.f;
+  }
+  term = warp_sum(term);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    block_part[blockIdx.x] = t;
+  }
+}
+__global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_part, int nb, float inv_2n, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += (double)block_part[b];
+    *loss = (float)(t * (double)inv_2n);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// backward
+// ----------------------------------------------------------------------------
+// TMEM map: [0,256) dZ accumulator (128 x D fp32), [256,384) S/P buffer 0, [384,512) S/P buffer 1.
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int D, int npanels, int nrb, int ntiles,
+                   const float* __restrict__ inv_r /*[ntiles*128], zero padded*/, const float* __restrict__ gscale,
+                   const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kPanelBytes * kMaxPanels;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPanelBytes * kMaxPanels * (1 + kStages));
+  uint64_t* full = bars;             // [2] V tile landed
+  uint64_t* empty = bars + 2;        // [2] V tile no longer needed (MMA2 done)
+  uint64_t* a_full = bars + 4;
+  uint64_t* a_empty = bars + 5;
+  uint64_t* s_full = bars + 6;       // [2] S = Z_U Z_V^T ready in TMEM
+  uint64_t* p_full = bars + 8;       // [2] P written back to TMEM (4 warp arrivals)
+  uint64_t* sp_empty = bars + 10;    // [2] MMA2 finished reading P
+  uint64_t* dz_full = bars + 12;
+  uint64_t* dz_empty = bars + 13;    // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&s_full[s], 1);
+      ptx::mbar_init(&p_full[s], 4);
+      ptx::mbar_init(&sp_empty[s], 1);
+    }
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1);
+    ptx::mbar_init(dz_full, 1);
+    ptx::mbar_init(dz_empty, 8);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmap);
+  }
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tile_bytes = (uint32_t)npanels * kPanelBytes;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t sphase = 0, aphase = 0;
+      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+        ptx::mbar_wait(a_empty, aphase ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
+        for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPanelBytes, &tmap, a_full, p * kPanelElems, rb * kBM);
+        aphase ^= 1;
+        for (int ct = 0; ct < ntiles; ++ct) {
+          ptx::mbar_wait(&empty[stage], sphase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          uint8_t* dst = sB + (size_t)stage * kPanelBytes * kMaxPanels;
+          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          if (++stage == kStages) { stage = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T     (A,B K-major)
+      const uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);        // dZ += P Z_V       (A tmem, B MN-major)
+      const uint32_t a_addr = ptx::smem_u32(sA);
+      uint32_t tcount = 0;  // global tile counter of this CTA: stage = buf = tcount & 1, phase = (tcount >> 1) & 1
+      uint32_t aphase = 0, dzphase = 0;
+      auto issue_mma1 = [&](uint32_t tc) {
+        const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
+        ptx::mbar_wait(&sp_empty[b], ph ^ 1u);
+        ptx::mbar_wait(&full[b], ph);
+        ptx::tc_fence_after();
+        const uint32_t b_addr = ptx::smem_u32(sB + (size_t)b * kPanelBytes * kMaxPanels);
+        const uint32_t d_tmem = tmem_base + 256u + b * 128u;
+        const int ksteps = npanels * 4;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t off = (uint32_t)(kk >> 2) * kPanelBytes + (uint32_t)(kk & 3) * 32u;
+          ptx::umma_ss(d_tmem, ptx::smem_desc_sw128(a_addr + off, 16, 1024), ptx::smem_desc_sw128(b_addr + off, 16, 1024), idesc1,
+                       kk > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&s_full[b]);
+      };
+      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+        ptx::mbar_wait(a_full, aphase);
+        aphase ^= 1;
+        ptx::mbar_wait(dz_empty, dzphase ^ 1);
+        issue_mma1(tcount);
+        for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+          if (ct + 1 < ntiles) issue_mma1(tcount + 1);
+          const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+          ptx::mbar_wait(&p_full[b], ph);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(sB + (size_t)b * kPanelBytes * kMaxPanels);
+          const uint32_t p_tmem = tmem_base + 256u + b * 128u;
+          // K = 128 rows of the V tile, 16 per step: MN-major B, 8-row groups 1024 B apart (SBO),
+          // 64-feature panels kPanelBytes apart (LBO)
+          for (int k = 0; k < kBN / 16; ++k) {
+            ptx::umma_ts(tmem_base, p_tmem + (uint32_t)k * 8u, ptx::smem_desc_sw128(b_addr + (uint32_t)k * 2048u, kPanelBytes, 1024),
+                         idesc2, (ct > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[b]);
+          ptx::umma_commit(&sp_empty[b]);
+        }
+        ptx::umma_commit(dz_full);
+        ptx::umma_commit(a_empty);
+        dzphase ^= 1;
+      }
+    }
+  } else {  // ---------------- softmax / epilogue warpgroups ----------------
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
+    uint32_t tcount = 0, dzphase = 0;
+    for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      const int row = rb * kBM + lrow;
+      const float cu = inv_r[row];  // padded with zeros beyond `rows`
+      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+        if ((int)(tcount & 1u) != wg) continue;
+        const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+        ptx::mbar_wait(&s_full[b], ph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = lane_base + 256u + b * 128u;
+        const bool diag = (ct == rb);
+        const float4* cvp = reinterpret_cast<const float4*>(inv_r + (size_t)ct * kBN);
+#pragma unroll
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 cv = __ldg(cvp + c * 8 + q);
+            float p0 = ex2(__uint_as_float(r[4 * q + 0])) * (cu + cv.x);
+            float p1 = ex2(__uint_as_float(r[4 * q + 1])) * (cu + cv.y);
+            float p2 = ex2(__uint_as_float(r[4 * q + 2])) * (cu + cv.z);
+            float p3 = ex2(__uint_as_float(r[4 * q + 3])) * (cu + cv.w);
+            if (diag) {
+              const int j = c * 32 + 4 * q;
+              if (j + 0 == lrow) p0 = 0.f;
+              if (j + 1 == lrow) p1 = 0.f;
+              if (j + 2 == lrow) p2 = 0.f;
+              if (j + 3 == lrow) p3 = 0.f;
+            }
+            pk[2 * q] = pack2(p0, p1);
+            pk[2 * q + 1] = pack2(p2, p3);
+          }
+          ptx::tmem_st16(taddr + c * 16, pk);  // P (bf16 pairs) aliases the S columns already consumed
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+      }
+      // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D)
+      ptx::mbar_wait(dz_full, dzphase);
+      dzphase ^= 1;
+      ptx::tc_fence_after();
+      const int half = D / 2;
+      const int pair = (row < N) ? row + N : row - N;
+      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (row < rows) {
+          const uint4* zp = reinterpret_cast<const uint4*>(z + (size_t)pair * D + c0);
+          float* out = dz + (size_t)row * D + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(__ldg(zp + q), f);
+            float4 o0, o1;
+            o0.x = gcoef * (__uint_as_float(r[8 * q + 0]) - 2.f * f[0]);
+            o0.y = gcoef * (__uint_as_float(r[8 * q + 1]) - 2.f * f[1]);
+            o0.z = gcoef * (__uint_as_float(r[8 * q + 2]) - 2.f * f[2]);
+            o0.w = gcoef * (__uint_as_float(r[8 * q + 3]) - 2.f * f[3]);
+            o1.x = gcoef * (__uint_as_float(r[8 * q + 4]) - 2.f * f[4]);
+            o1.y = gcoef * (__uint_as_float(r[8 * q + 5]) - 2.f * f[5]);
+            o1.z = gcoef * (__uint_as_float(r[8 * q + 6]) - 2.f * f[6]);
+            o1.w = gcoef * (__uint_as_float(r[8 * q + 7]) - 2.f * f[7]);
+            *reinterpret_cast<float4*>(out + 8 * q) = o0;
+            *reinterpret_cast<float4*>(out + 8 * q + 4) = o1;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dz_empty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Z is [rows, D] bf16 row-major; box = 64 columns (128 B) x 128 rows, 128-byte swizzle, OOB rows read as zero.
+static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return BMKG_ERR_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kPanelElems, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(z), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? BMKG_OK : BMKG_ERR_DRIVER;
+}
+
+static Schedule make_schedule(int64_t rows) {
+  Schedule s;
+  s.nrb = (int)ceil_div(rows, kBM);
+  s.ntiles = (int)ceil_div(rows, kBN);
+  int chunks = (int)ceil_div(2 * kNumSMs, s.nrb);  // aim for >= 2 work items per SM
+  if (chunks > s.ntiles) chunks = s.ntiles;
+  if (chunks < 1) chunks = 1;
+  s.tiles_per_chunk = (int)ceil_div(s.ntiles, chunks);
+  s.nchunks = (int)ceil_div(s.ntiles, s.tiles_per_chunk);
+  return s;
+}
+
+}  // namespace nce
+}  // namespace bmkg
+
+using namespace bmkg;
+using namespace bmkg::nce;
+
+extern "C" {
+
+int64_t bmkg_infonce_padded_rows(int64_t N) { return ceil_div(2 * N, kBN) * kBN; }
+
+size_t bmkg_infonce_workspace_bytes(int64_t N, int D) {
+  (void)D;
+  const int64_t rows = 2 * N;
+  Schedule s = make_schedule(rows);
+  const int64_t rp = bmkg_infonce_padded_rows(N);
+  WsCarver c(nullptr);
+  c.take<float>((size_t)2 * s.nchunks * rp);
+  c.take<float>((size_t)ceil_div(rp, 256));
+  return c.used();
+}
+
+int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* inv_r, void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(z_bf16 && loss && inv_r && N > 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
+  BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(z_bf16), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes(N, D), BMKG_ERR_WORKSPACE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = 2 * N;
+  const int64_t rp = bmkg_infonce_padded_rows(N);
+  Schedule s = make_schedule(rows);
+  WsCarver c(ws);
+  float* partial = c.take<float>((size_t)2 * s.nchunks * rp);
+  const int nb = (int)ceil_div(rp, 256);
+  float* block_part = c.take<float>(nb);
+
+  CUtensorMap tmap;
+  int rc = make_z_tensormap(&tmap, z_bf16, rows, D);
+  if (rc != BMKG_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return BMKG_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int n_items = s.nrb * s.nchunks;
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  infonce_fwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, (int)rows, D / kPanelElems, s, (int)rp, partial);
+  BMKG_CHECK_LAUNCH();
+  const float npad = (float)(s.ntiles * kBN - rows);
+  infonce_finalize_rows_kernel<<<nb, 256, 0, st>>>(partial, 2 * s.nchunks, (int)rp, (int)rows, (int)N, D, npad,
+                                                   static_cast<const __nv_bfloat16*>(z_bf16), inv_r, block_part);
+  infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nb, 1.0f / (2.0f * (float)N), loss);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, float* dz, void* stream) {
+  BMKG_REQUIRE(z_bf16 && inv_r && gscale && dz && N > 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
+  BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(inv_r), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = 2 * N;
+  const int nrb = (int)ceil_div(rows, kBM), ntiles = (int)ceil_div(rows, kBN);
+  CUtensorMap tmap;
+  int rc = make_z_tensormap(&tmap, z_bf16, rows, D);
+  if (rc != BMKG_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+      return BMKG_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int grid = nrb < kNumSMs ? nrb : kNumSMs;
+  infonce_bwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, (int)rows, (int)N, D, D / kPanelElems, nrb, ntiles, inv_r, gscale,
+                                                         static_cast<const __nv_bfloat16*>(z_bf16), dz);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""Random draws of the GCL step, in the reference's order.
+
+``DeviceDraws`` is the product default: feature / edge masks are drawn by torch
+on the tensor's device exactly as PyG's ``mask_feature`` / ``dropout_edge`` do
+(``torch.rand_like(x) >= p`` / ``torch.rand(E) >= p``), ``randperm`` and the GGD
+coin come from the CPU generator as in the reference, and encoder dropout is a
+counter-based stream evaluated inside the aggregation kernel (seeded from
+``torch.initial_seed()``).  ``ReplayDraws`` feeds recorded draws back (tests).
+"""
+from __future__ import annotations
+
+import torch
+
+_MASK64 = 0xFFFFFFFFFFFFFFFF
+
+
+def _splitmix(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _MASK64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK64
+    return z ^ (z >> 31)
+
+
+def hash_keep_mask(seed: int, numel: int, p: float) -> torch.Tensor:
+    """Host mirror of csrc/common.cuh:hash_keep - keep[i] = hash_u32(seed, i) >= p * 2^32."""
+    import numpy as np
+
+    idx = np.arange(numel, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed & _MASK64)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    u = (z >> np.uint64(32)).astype(np.uint64)
+    thr = np.uint64(int(p * 4294967296.0))
+    return torch.from_numpy(u >= thr)
+
+
+class DeviceDraws:
+    def __init__(self):
+        self._counter = 0
+
+    def feature_mask(self, x, p):
+        return torch.rand_like(x, dtype=torch.float32) >= p
+
+    def edge_mask(self, edge_index, p):
+        return torch.rand(edge_index.size(1), device=edge_index.device) >= p
+
+    def dropout(self, shape, p, device):
+        """-> (seed, explicit_keep_mask_or_None) for the fused aggregation epilogue."""
+        self._counter += 1
+        return _splitmix(torch.initial_seed() ^ _splitmix(self._counter)), None
+
+    def randperm(self, n):
+        return torch.randperm(n)
+
+    def coin(self):
+        return float(torch.rand(1).item())
+
+
+class ReplayDraws:
+    """Replays (kind, value) records, e.g. the ``draws`` list of a golden fixture."""
+
+    def __init__(self, log, device):
+        self.log, self.i, self.device = list(log), 0, device
+
+    def _next(self, kind):
+        k, v = self.log[self.i]
+        if k != kind:
+            raise AssertionError(f"draw order mismatch: wanted {kind}, recorded {k} at position {self.i}")
+        self.i += 1
+        return v
+
+    def feature_mask(self, x, p):
+        return self._next("feature_mask").to(self.device)
+
+    def edge_mask(self, edge_index, p):
+        return self._next("edge_mask").to(self.device)
+
+    def dropout(self, shape, p, device):
+        return 0, self._next("dropout_mask").to(self.device)
+
+    def randperm(self, n):
+        return self._next("randperm")
+
+    def coin(self):
+        return self._next("coin")
+
+
+def set_draws(module: torch.nn.Module, draws) -> torch.nn.Module:
+    for m in module.modules():
+        if hasattr(m, "draws"):
+            m.draws = draws
+    return module

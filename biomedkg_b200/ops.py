@@ -1,0 +1,462 @@
+"""Tensor-level wrappers and autograd Functions over the C-ABI kernels.
+
+Everything here launches hand-written sm_100a kernels from libbmkg_b200.so on the
+current CUDA stream with raw ``data_ptr()`` arguments; PyTorch only owns memory,
+streams and autograd bookkeeping.  The dense Linear layers (X @ W^T) go to
+``torch.mm`` on bf16 operands (cuBLAS - a plain library GEMM).
+No CPU path exists: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _cabi
+from ._cabi import call, lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("biomedkg_b200 kernels are CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 (fp32 accumulate, no bf16 rounding of the result)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:  # older torch: no out_dtype
+        return torch.mm(a, b).float()
+
+
+# ---------------------------------------------------------------------------
+# graph indexing
+# ---------------------------------------------------------------------------
+class _Sorted:
+    __slots__ = ("major", "minor", "perm", "rowptr_raw", "split")
+
+
+class SortedGraph:
+    """edge_index sorted once by (dst,src) and by (src,dst); parent of every view."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        _need_cuda(edge_index)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
+        self.edge_index = edge_index.contiguous()
+        self.N, self.E = int(num_nodes), int(edge_index.size(1))
+        dev = edge_index.device
+        ws = _ws(lib.bmkg_edge_sort_workspace_bytes(self.N, self.E), dev)
+        self.by = []
+        for by_src in (0, 1):
+            s = _Sorted()
+            s.major = torch.empty(self.E, dtype=torch.int32, device=dev)
+            s.minor = torch.empty(self.E, dtype=torch.int32, device=dev)
+            s.perm = torch.empty(self.E, dtype=torch.int32, device=dev)
+            s.rowptr_raw = torch.empty(self.N + 1, dtype=torch.int32, device=dev)
+            s.split = torch.empty(self.N, dtype=torch.int32, device=dev)
+            call("bmkg_edge_sort", _p(self.edge_index), self.E, self.N, by_src, _p(s.major), _p(s.minor), _p(s.perm),
+                 _p(s.rowptr_raw), _p(s.split), _p(ws), ws.numel(), _stream())
+            self.by.append(s)
+
+    def view(self, keep: torch.Tensor | None = None, want_perm: bool = False) -> "GraphView":
+        return GraphView(self, keep, want_perm)
+
+
+class GraphView:
+    """Canonical CSR (by destination) + CSC (by source) of one augmented view,
+    self-loops normalised as PyG gcn_norm does, plus dis = indegree^-1/2."""
+
+    def __init__(self, sg: SortedGraph, keep: torch.Tensor | None, want_perm: bool = False):
+        dev = sg.edge_index.device
+        N, E = sg.N, sg.E
+        if keep is not None:
+            _need_cuda(keep)
+            if keep.numel() != E:
+                raise ValueError("keep mask must have one entry per edge")
+            keep = keep.contiguous().view(torch.uint8) if keep.dtype == torch.bool else keep.to(torch.uint8).contiguous()
+        self.N, self.cap = N, E + N
+        ws = _ws(lib.bmkg_csr_filter_workspace_bytes(N, E), dev)
+        self.rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        self.colind = torch.empty(E + N, dtype=torch.int32, device=dev)
+        self.perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
+        self.dis = torch.empty(N, dtype=torch.float32, device=dev)
+        self.nnz = torch.empty(1, dtype=torch.int32, device=dev)
+        s = sg.by[0]
+        call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
+             _p(sg.edge_index), E, N, _p(self.rowptr), _p(self.colind), _p(self.perm), _p(self.dis), _p(self.nnz), _p(ws),
+             ws.numel(), _stream())
+        self.csc_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        self.csc_colind = torch.empty(E + N, dtype=torch.int32, device=dev)
+        self.csc_perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
+        s = sg.by[1]
+        call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
+             _p(sg.edge_index), E, N, _p(self.csc_rowptr), _p(self.csc_colind), _p(self.csc_perm), None, None, _p(ws),
+             ws.numel(), _stream())
+
+
+_GRAPH_CACHE: dict = {}
+
+
+def sorted_graph(edge_index: torch.Tensor, num_nodes: int, cache: bool = True) -> SortedGraph:
+    """Sort once per (tensor identity, version): full-graph training reuses the
+    same edge_index tensor every step, so the radix sort runs once."""
+    if not cache:
+        return SortedGraph(edge_index, num_nodes)
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), edge_index.device)
+    sg = _GRAPH_CACHE.get(key)
+    if sg is None:
+        if len(_GRAPH_CACHE) >= 8:
+            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+        sg = SortedGraph(edge_index, num_nodes)
+        _GRAPH_CACHE[key] = sg
+    return sg
+
+
+def as_view(graph, num_nodes: int) -> GraphView:
+    if isinstance(graph, GraphView):
+        return graph
+    return sorted_graph(graph, num_nodes).view(None)
+
+
+# ---------------------------------------------------------------------------
+# raw kernel wrappers
+# ---------------------------------------------------------------------------
+def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False):
+    _need_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    N, C = x.shape
+    out = torch.empty(N, C, dtype=torch.float32 if out_fp32 else BF16, device=x.device)
+    if drop_keep is not None:
+        drop_keep = drop_keep.contiguous().view(torch.uint8) if drop_keep.dtype == torch.bool else drop_keep.contiguous()
+    call("bmkg_gcn_aggregate", _p(rowptr), _p(colind), _p(dis), _p(x), N, C, _p(bias), int(relu), float(drop_p),
+         int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), _stream())
+    return out
+
+
+def colsum(z: torch.Tensor, row_weight: torch.Tensor | None = None) -> torch.Tensor:
+    _need_cuda(z)
+    z = z.contiguous()
+    N, C = z.shape
+    out = torch.empty(C, dtype=torch.float32, device=z.device)
+    ws = _ws(lib.bmkg_colsum_workspace_bytes(N, C), z.device)
+    call("bmkg_colsum", _p(z), _p(row_weight), N, C, _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def _as_u8(m):
+    if m is None:
+        return None
+    return m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m.contiguous()
+
+
+class _MaskCastFn(torch.autograd.Function):
+    """x fp32 -> (plain, masked1, masked2) bf16 in one pass (mask_feature mode="all")."""
+
+    @staticmethod
+    def forward(ctx, x, keep1, keep2, want_plain):
+        _need_cuda(x)
+        x = x.contiguous()
+        keep1, keep2 = _as_u8(keep1), _as_u8(keep2)
+        x0 = torch.empty_like(x, dtype=BF16) if want_plain else None
+        x1 = torch.empty_like(x, dtype=BF16) if keep1 is not None else None
+        x2 = torch.empty_like(x, dtype=BF16) if keep2 is not None else None
+        call("bmkg_mask_cast", _p(x), _p(keep1), _p(keep2), x.numel(), _p(x0), _p(x1), _p(x2), _stream())
+        ctx.save_for_backward(keep1, keep2)
+        return x0, x1, x2
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2):
+        keep1, keep2 = ctx.saved_tensors
+        g = None
+        for gi, k in ((g0, None), (g1, keep1), (g2, keep2)):
+            if gi is None:
+                continue
+            t = gi.float() if k is None else gi.float() * k.view(gi.shape)
+            g = t if g is None else g + t
+        return g, None, None, None
+
+
+def mask_cast(x, keep1=None, keep2=None, want_plain=True):
+    if x.numel() % 4:
+        raise ValueError("feature matrix size must be a multiple of 4")
+    return _MaskCastFn.apply(x, keep1, keep2, want_plain)
+
+
+class _ModalityMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous()
+        N, M, Fdim = x.shape
+        out = torch.empty(N, Fdim, dtype=torch.float32, device=x.device)
+        call("bmkg_modality_mean", _p(x), N, M, Fdim, _p(out), None, _stream())
+        ctx.M = M
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g / ctx.M).unsqueeze(1).expand(-1, ctx.M, -1)
+
+
+def modality_mean(x):
+    return _ModalityMeanFn.apply(x.float())
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on bf16 tensor-core GEMMs with fp32 accumulate/out (library GEMM)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_bf16):
+        x16 = x if x.dtype == BF16 else x.to(BF16)
+        w16 = weight.to(BF16)
+        if out_bf16:
+            y = torch.mm(x16, w16.t())
+            if bias is not None:
+                y = y + bias.to(BF16)
+        else:
+            y = _mm_f32(x16, w16.t())
+            if bias is not None:
+                y = y + bias
+        ctx.save_for_backward(x16, w16)
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x16, w16 = ctx.saved_tensors
+        g16 = g.contiguous() if g.dtype == BF16 else g.to(BF16)
+        dx = torch.mm(g16, w16).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        dw = _mm_f32(g16.t(), x16) if ctx.needs_input_grad[1] else None
+        db = colsum(g.float()) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, out_bf16=False):
+    lead = x.shape[:-1]
+    y = _LinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias, out_bf16)
+    return y.reshape(*lead, weight.shape[0])
+
+
+# ---------------------------------------------------------------------------
+# GCN layer
+# ---------------------------------------------------------------------------
+class _GCNLayerFn(torch.autograd.Function):
+    """One GCNConv (+ReLU+dropout) of encoder.py:153-162: X W^T (library GEMM) then the
+    fused CSR aggregation kernel; backward = fused ReLU/dropout/bias-grad kernel, the same
+    aggregation kernel on the CSC, and two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32):
+        _need_cuda(x)
+        assert x.dtype == BF16
+        x = x.contiguous()
+        w16 = weight.to(BF16)
+        xw = torch.mm(x, w16.t())
+        y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32)
+        ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
+        ctx.save_for_backward(x, w16, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16, y = ctx.saved_tensors
+        view = ctx.view
+        gy = gy.contiguous()
+        N, C = gy.shape
+        if ctx.relu:
+            gy16 = gy if gy.dtype == BF16 else gy.to(BF16)
+            gpre = torch.empty(N, C, dtype=BF16, device=gy.device)
+            dbias = torch.empty(C, dtype=torch.float32, device=gy.device)
+            ws = _ws(lib.bmkg_colsum_workspace_bytes(N, C), gy.device)
+            scale = 1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0 else 1.0
+            call("bmkg_relu_dropout_bwd", _p(gy16), _p(y), float(scale), N, C, _p(gpre), _p(dbias), _p(ws), ws.numel(), _stream())
+        else:
+            dbias = colsum(gy.float())
+            gpre = gy if gy.dtype == BF16 else gy.to(BF16)
+        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre)
+        dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
+        dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
+        return dx, dw, dbias, None, None, None, None, None, None
+
+
+def gcn_layer(x, weight, bias, view, relu, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False):
+    return _GCNLayerFn.apply(x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32)
+
+
+# ---------------------------------------------------------------------------
+# heads
+# ---------------------------------------------------------------------------
+class _RowDotFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, v):
+        _need_cuda(z, v)
+        z, v = z.contiguous().float(), v.contiguous().float().view(-1)
+        N, C = z.shape
+        out = torch.empty(N, dtype=torch.float32, device=z.device)
+        call("bmkg_rowdot", _p(z), _p(v), N, C, _p(out), _stream())
+        ctx.save_for_backward(z, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, v = ctx.saved_tensors
+        g = g.contiguous().float()
+        N, C = z.shape
+        dz = dv = None
+        if ctx.needs_input_grad[0]:
+            dz = torch.empty_like(z)
+            call("bmkg_rowdot_bwd", _p(g), _p(v), N, C, _p(dz), _stream())
+        if ctx.needs_input_grad[1]:
+            dv = colsum(z, g)
+        return dz, dv
+
+
+def rowdot(z, v):
+    return _RowDotFn.apply(z, v)
+
+
+class _SoftplusPairFn(torch.autograd.Function):
+    """sum softplus(-s_pos) + sum softplus(s_neg), deterministic."""
+
+    @staticmethod
+    def forward(ctx, sp, sn):
+        _need_cuda(sp, sn)
+        sp, sn = sp.contiguous().float(), sn.contiguous().float()
+        out = torch.empty((), dtype=torch.float32, device=sp.device)
+        ws = _ws(lib.bmkg_softplus_pair_workspace_bytes(sp.numel()), sp.device)
+        call("bmkg_softplus_pair_sum", _p(sp), _p(sn), sp.numel(), _p(out), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(sp, sn)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sp, sn = ctx.saved_tensors
+        g = g.contiguous().float()
+        dsp, dsn = torch.empty_like(sp), torch.empty_like(sn)
+        call("bmkg_softplus_pair_bwd", _p(sp), _p(sn), _p(g), sp.numel(), _p(dsp), _p(dsn), _stream())
+        return dsp, dsn
+
+
+def softplus_pair_sum(sp, sn):
+    return _SoftplusPairFn.apply(sp, sn)
+
+
+class _ColMeanSigmoidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        _need_cuda(z)
+        z = z.contiguous().float()
+        N, C = z.shape
+        s = torch.empty(1, C, dtype=torch.float32, device=z.device)
+        ws = _ws(lib.bmkg_colsum_workspace_bytes(N, C) + 4 * C, z.device)
+        call("bmkg_colmean_sigmoid", _p(z), N, C, _p(s), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(s)
+        ctx.N = N
+        return s
+
+    @staticmethod
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        return (g * s * (1.0 - s) / ctx.N).expand(ctx.N, -1)
+
+
+def colmean_sigmoid(z):
+    return _ColMeanSigmoidFn.apply(z)
+
+
+# ---------------------------------------------------------------------------
+# fusion attention core
+# ---------------------------------------------------------------------------
+class _FusionAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, N, M, E):
+        _need_cuda(qkv)
+        assert qkv.dtype == BF16 and qkv.is_contiguous()
+        out = torch.empty(N, E, dtype=torch.float32, device=qkv.device)
+        probs = torch.empty(N, M, M, dtype=torch.float32, device=qkv.device)
+        call("bmkg_fusion_attn_fwd", _p(qkv), N, M, E, _p(out), _p(probs), _stream())
+        ctx.save_for_backward(qkv, probs)
+        ctx.dims = (N, M, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, probs = ctx.saved_tensors
+        N, M, E = ctx.dims
+        g = g.contiguous().float()
+        dqkv = torch.empty_like(qkv)
+        call("bmkg_fusion_attn_bwd", _p(qkv), _p(probs), _p(g), N, M, E, _p(dqkv), _stream())
+        return dqkv, None, None, None
+
+
+def fusion_attention(qkv, N, M, E):
+    return _FusionAttnFn.apply(qkv, N, M, E)
+
+
+# ---------------------------------------------------------------------------
+# fused InfoNCE
+# ---------------------------------------------------------------------------
+LOG2E = 1.4426950408889634
+
+
+class _InfoNCEFn(torch.autograd.Function):
+    """DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True)(h1, h2)."""
+
+    @staticmethod
+    def forward(ctx, h1, h2, tau):
+        _need_cuda(h1, h2)
+        h1, h2 = h1.contiguous().float(), h2.contiguous().float()
+        N, D = h1.shape
+        dev = h1.device
+        scale = math.sqrt(LOG2E / tau)
+        z = torch.empty(2 * N, D, dtype=BF16, device=dev)
+        inv_norm = torch.empty(2 * N, dtype=torch.float32, device=dev)
+        call("bmkg_l2norm_scale", _p(h1), N, D, scale, _p(z), _p(inv_norm), _stream())
+        call("bmkg_l2norm_scale", _p(h2), N, D, scale, z.data_ptr() + N * D * 2, inv_norm.data_ptr() + N * 4, _stream())
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        inv_r = torch.empty(lib.bmkg_infonce_padded_rows(N), dtype=torch.float32, device=dev)
+        ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
+        call("bmkg_infonce_fwd", _p(z), N, D, _p(loss), _p(inv_r), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(h1, h2, z, inv_norm, inv_r)
+        ctx.scale = scale
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        h1, h2, z, inv_norm, inv_r = ctx.saved_tensors
+        N, D = h1.shape
+        g = g.contiguous().float()
+        dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
+        call("bmkg_infonce_bwd", _p(z), _p(inv_r), _p(g), N, D, _p(dz), _stream())
+        dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
+        call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())
+        call("bmkg_l2norm_scale_bwd", _p(h2), inv_norm.data_ptr() + N * 4, dz.data_ptr() + N * D * 4, N, D, ctx.scale, _p(dh2),
+             _stream())
+        return dh1, dh2, None
+
+
+def infonce_loss(h1, h2, tau=0.2):
+    if h1.shape != h2.shape or h1.dim() != 2:
+        raise ValueError("h1 and h2 must both be [N, D]")
+    return _InfoNCEFn.apply(h1, h2, float(tau))
+
+
+def launch_count() -> int:
+    return _cabi.call_count

@@ -1,0 +1,124 @@
+/* bmkg_b200 - C-ABI of the B200-native GCL training-step kernels.
+ *
+ * The reference (HySonLab/BioMedKG) has no FFI: its extension seam is the
+ * torch.nn.Module surface (biomedkg/model/*, biomedkg/utils/fusion.py,
+ * biomedkg/gcl_module.py) and every kernel below replaces a third-party library
+ * call reached from that surface.  Each entry point cites the reference call
+ * site it serves.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless noted;
+ *   - the caller allocates every output and workspace; kernels never allocate;
+ *   - return 0 (BMKG_OK) or a negative error code; nothing throws;
+ *   - stateless, re-entrant, stream-ordered on `stream` (a cudaStream_t), no
+ *     internal synchronisation; callable from any host thread;
+ *   - bf16 tensors are row-major, 16-byte aligned; index arrays are int32 on the
+ *     device, int64 edge_index [2,E] at the boundary (as PyG / the reference).
+ */
+#ifndef BMKG_B200_H_
+#define BMKG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMKG_ABI_VERSION 1
+
+int bmkg_abi_version(void);
+const char* bmkg_error_string(int code);
+
+/* ---- G1: edge_index -> sorted parent graph ------------------------------------------
+ * Replaces the per-call COO handling inside PyG GCNConv (biomedkg/model/encoder.py:155,160).
+ * Stable sort of the E edges by key (major, minor); by_src = 0 sorts by destination (CSR
+ * for the forward aggregation), by_src = 1 by source (CSC for the transposed backward).
+ * Outputs: major_sorted/minor_sorted/perm_sorted [E], rowptr_raw [N+1], selfsplit [N]
+ * (first sorted position of row i whose minor >= i). */
+size_t bmkg_edge_sort_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int bmkg_edge_sort(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int by_src, int32_t* major_sorted,
+                   int32_t* minor_sorted, int32_t* perm_sorted, int32_t* rowptr_raw, int32_t* selfsplit, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* ---- G2: per-view canonical CSR ----------------------------------------------------------
+ * Replaces torch_geometric.utils.dropout_edge's edge_index[:, mask] (biomedkg/model/gcl.py:42-43,76)
+ * followed by gcn_norm's remove/add self-loops and degree (PyG GCNConv).
+ * keep: optional uint8 [E] mask in ORIGINAL edge order (NULL = keep all).  Outputs the canonical CSR
+ * of the view's edge list ei' (kept non-self edges in order, then one self-loop per node):
+ * rowptr [N+1], colind [E+N capacity], optional perm [E+N] (position in ei'; needs edge_index),
+ * optional dis [N] = indegree^-1/2 (fp32), optional nnz_out (device int32). Bit-exact. */
+size_t bmkg_csr_filter_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, const int32_t* perm_sorted,
+                    const int32_t* rowptr_raw, const int32_t* selfsplit, const uint8_t* keep, const int64_t* edge_index,
+                    int64_t num_edges, int64_t num_nodes, int32_t* rowptr, int32_t* colind, int32_t* perm, float* dis,
+                    int32_t* nnz_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A1/A2: GCN aggregation -----------------------------------------------------------------
+ * Replaces GCNConv.propagate + bias (+ F.relu, F.dropout of encoder.py:155-158):
+ *   out[r] = dropout(relu( dis[r] * sum_{k in row r} dis[colind[k]] * x[colind[k]] + bias ))
+ * x bf16 [N,C]; out bf16 or fp32 [N,C]; C % 8 == 0, C <= 1024.  With a CSC graph and no
+ * epilogue this is the transposed backward.  drop_keep: optional explicit uint8 [N,C] keep mask,
+ * otherwise (drop_p > 0) the counter-based stream hash(drop_seed, r*C+c) decides. */
+int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* x_bf16, int64_t num_nodes,
+                       int channels, const float* bias, int relu, float drop_p, uint64_t drop_seed, const uint8_t* drop_keep,
+                       void* out, int out_is_fp32, void* stream);
+
+/* ---- elementwise / small reductions -------------------------------------------------------
+ * bmkg_mask_cast: torch_geometric.utils.mask_feature(mode="all") (model/gcl.py:40-41,75) fused with the
+ *   fp32->bf16 cast: x fp32 [n] -> x0 (plain), x1 (keep1), x2 (keep2), any of them NULL; n % 4 == 0.
+ * bmkg_modality_mean: torch.mean(x, dim=1) of gcl_module.py:47-48; x fp32 [N,M,F].
+ * bmkg_relu_dropout_bwd: backward of encoder.py:155-158, g_pre = (y>0) ? g_y*scale : 0, dbias = colsum(g_pre).
+ * bmkg_colsum: deterministic (optionally row-weighted) column sums of fp32 [N,C].
+ * bmkg_l2norm_scale(_bwd): F.normalize of PyGCL's _similarity fused with the sqrt(log2e/tau) scale. */
+int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, int64_t n, void* x0_bf16, void* x1_bf16,
+                   void* x2_bf16, void* stream);
+int bmkg_modality_mean(const float* x, int64_t num_nodes, int modalities, int features, float* out_f32, void* out_bf16,
+                       void* stream);
+size_t bmkg_colsum_workspace_bytes(int64_t num_rows, int channels);
+int bmkg_relu_dropout_bwd(const void* gy_bf16, const void* y_bf16, float scale, int64_t num_rows, int channels,
+                          void* gpre_bf16, float* dbias, void* ws, size_t ws_bytes, void* stream);
+int bmkg_colsum(const float* z, const float* row_weight, int64_t num_rows, int channels, float* out, void* ws, size_t ws_bytes,
+                void* stream);
+int bmkg_l2norm_scale(const float* h, int64_t num_rows, int dim, float scale, void* z_bf16, float* inv_norm, void* stream);
+int bmkg_l2norm_scale_bwd(const float* h, const float* inv_norm, const float* dz, int64_t num_rows, int dim, float scale,
+                          float* dh, void* stream);
+
+/* ---- D1-D3: DGI / GGD heads ---------------------------------------------------------------
+ * DGI.summary (model/gcl.py:19-21), SingleBranchContrast(JSD,"G2L") (gcl_module.py:127,142),
+ * GGD head (model/gcl.py:87-91) and BCEWithLogits (gcl_module.py:231-233). */
+int bmkg_colmean_sigmoid(const float* z, int64_t num_rows, int channels, float* summary, void* ws, size_t ws_bytes,
+                         void* stream);
+int bmkg_rowdot(const float* z, const float* v, int64_t num_rows, int channels, float* out, void* stream);
+int bmkg_rowdot_bwd(const float* g, const float* v, int64_t num_rows, int channels, float* dz, void* stream);
+size_t bmkg_softplus_pair_workspace_bytes(int64_t n);
+int bmkg_softplus_pair_sum(const float* s_pos, const float* s_neg, int64_t n, float* out, void* ws, size_t ws_bytes,
+                           void* stream);
+int bmkg_softplus_pair_bwd(const float* s_pos, const float* s_neg, const float* gscale, int64_t n, float* d_pos, float* d_neg,
+                           void* stream);
+
+/* ---- F1: modality-fusion attention core ---------------------------------------------------
+ * F.scaled_dot_product_attention over the modality axis + mean (biomedkg/utils/fusion.py:22-29).
+ * qkv bf16 [N*M, 3E] (row = [q|k|v] of one (node, modality)); out fp32 [N,E]; probs fp32 [N,M,M]
+ * saved for the backward; M <= 4, E % 8 == 0. */
+int bmkg_fusion_attn_fwd(const void* qkv_bf16, int64_t num_nodes, int modalities, int embed, float* out, float* probs,
+                         void* stream);
+int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* probs, const float* dout, int64_t num_nodes, int modalities,
+                         int embed, void* dqkv_bf16, void* stream);
+
+/* ---- I1/I2: fused GRACE InfoNCE (tcgen05 / TMEM / TMA) -----------------------------------
+ * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).
+ * z bf16 [2N, D]: rows [0,N) = normalize(h1) * sqrt(log2e/tau), rows [N,2N) = same for h2
+ * (bmkg_l2norm_scale).  D in {64,128,192,256}.  inv_r: fp32 [bmkg_infonce_padded_rows(N)].
+ * fwd writes the scalar loss and 1/R_u; bwd writes dL/dz fp32 [2N, D] scaled by *gscale. */
+int64_t bmkg_infonce_padded_rows(int64_t num_nodes);
+size_t bmkg_infonce_workspace_bytes(int64_t num_nodes, int dim);
+int bmkg_infonce_fwd(const void* z_bf16, int64_t num_nodes, int dim, float* loss, float* inv_r, void* ws, size_t ws_bytes,
+                     void* stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t num_nodes, int dim, float* dz,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMKG_B200_H_ */

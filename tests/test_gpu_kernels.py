@@ -1,0 +1,170 @@
+"""Kernel-level parity vs the oracle: aggregation fwd/bwd, elementwise, heads, fusion, InfoNCE.
+Tolerances: bf16 storage / fp32 accumulate -> relative Frobenius error <= 1e-2 for tensors,
+<= 1e-3 relative for scalar losses (BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import models as om
+from oracle import pyg, pygcl
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g, dtype=torch.int64)
+    if e > 8:
+        ei[1, :3] = ei[0, :3]
+        ei[:, -3:] = ei[:, :3]
+    return ei
+
+
+@pytest.mark.parametrize("n,e,c", [(50, 300, 64), (333, 5000, 256), (1000, 20000, 256), (200, 1000, 512), (64, 0, 256)])
+def test_gcn_aggregate_forward(n, e, c):
+    from biomedkg_b200 import ops
+
+    ei = _graph(n, e, n + e)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, c, generator=g).bfloat16()
+    bias = torch.randn(c, generator=g)
+    view = ops.SortedGraph(ei.to(DEV), n).view(None)
+    out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), relu=False, out_fp32=True)
+    ref = pyg.gcn_dense_adj(ei, n) @ x.double() + bias.double()
+    assert rel_err(out, ref) < 1e-5           # same bf16 inputs, fp32 accumulate: only summation-order noise
+    # fused ReLU + explicit dropout mask epilogue, bf16 out
+    keep = torch.rand(n, c, generator=g) >= 0.2
+    out2 = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), relu=True, drop_p=0.2, drop_keep=keep.to(DEV))
+    ref2 = torch.relu(ref) * keep / 0.8
+    assert rel_err(out2.float(), ref2) < 5e-3   # bf16 output rounding
+    # transposed (CSC) aggregation == A_hat^T
+    outT = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, x.to(DEV), out_fp32=True)
+    assert rel_err(outT, pyg.gcn_dense_adj(ei, n).t() @ x.double()) < 1e-5
+
+
+def test_gcn_aggregate_hashed_dropout_matches_host_mirror():
+    from biomedkg_b200 import ops
+    from biomedkg_b200.draws import hash_keep_mask
+
+    n, c, seed = 100, 256, 0xDEADBEEF12345
+    ei = _graph(n, 800, 3)
+    x = torch.randn(n, c).bfloat16()
+    view = ops.SortedGraph(ei.to(DEV), n).view(None)
+    a = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), relu=True, drop_p=0.2, drop_seed=seed)
+    keep = hash_keep_mask(seed, n * c, 0.2).view(n, c)
+    b = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), relu=True, drop_p=0.2, drop_keep=keep.to(DEV))
+    assert torch.equal(a, b)
+    assert abs(float(keep.float().mean()) - 0.8) < 0.02
+
+
+def test_gcn_layer_autograd_matches_oracle():
+    from biomedkg_b200 import ops
+
+    n, e, cin, c = 300, 4000, 96, 256
+    ei = _graph(n, e, 11)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, cin, generator=g)
+    w = torch.randn(c, cin, generator=g) * 0.1
+    b = torch.randn(c, generator=g) * 0.1
+    keep = torch.rand(n, c, generator=g) >= 0.2
+    gy = torch.randn(n, c, generator=g)
+    # oracle in fp64 on the same bf16-rounded inputs
+    xd = x.bfloat16().double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    yd = torch.relu(pyg.gcn_conv(xd, ei, wd, bd)) * keep / 0.8
+    yd.backward(gy.double())
+    view = ops.SortedGraph(ei.to(DEV), n).view(None)
+    xc = x.bfloat16().to(DEV).requires_grad_(True)
+    wc = w.to(DEV).requires_grad_(True)
+    bc = b.to(DEV).requires_grad_(True)
+    yc = ops.gcn_layer(xc, wc, bc, view, True, 0.2, 0, keep.to(DEV), False)
+    yc.backward(gy.to(DEV).bfloat16())
+    assert rel_err(yc.float(), yd) < 1e-2
+    assert rel_err(wc.grad, wd.grad) < 1e-2
+    assert rel_err(bc.grad, bd.grad) < 1e-2
+    assert rel_err(xc.grad.float(), xd.grad) < 1e-2
+
+
+def test_mask_cast_and_modality_mean():
+    from biomedkg_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(77, 768, generator=g)
+    k1, k2 = torch.rand(77, 768, generator=g) >= 0.4, torch.rand(77, 768, generator=g) >= 0.4
+    x0, x1, x2 = ops.mask_cast(x.to(DEV), k1.to(DEV), k2.to(DEV))
+    assert torch.equal(x0.cpu(), x.bfloat16())
+    assert torch.equal(x1.cpu(), pyg.mask_feature(x, 0.4, "all", rand=k1.float())[0].bfloat16())   # rand>=p <=> keep
+    assert torch.equal(x2.cpu(), x.masked_fill(~k2, 0).bfloat16())
+    x3 = torch.randn(33, 3, 768, generator=g)
+    assert torch.allclose(ops.modality_mean(x3.to(DEV)).cpu(), x3.mean(1), atol=1e-6)
+
+
+@pytest.mark.parametrize("n,c", [(10, 64), (1000, 256), (5003, 256)])
+def test_heads(n, c):
+    from biomedkg_b200 import losses, ops
+
+    g = torch.Generator().manual_seed(n)
+    z, zn = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+    wp, bp = torch.randn(c, c, generator=g) / math.sqrt(c), torch.randn(c, generator=g) * 0.1
+    # DGI: summary -> project -> JSD
+    zd, znd, wd = z.double().requires_grad_(True), zn.double().requires_grad_(True), wp.double().requires_grad_(True)
+    gd = om.DGI.summary(zd) @ wd.t() + bp.double()
+    ld = pygcl.jsd_g2l_as_written(zd, gd, znd)
+    ld.backward()
+    zc, znc, wc = z.to(DEV).requires_grad_(True), zn.to(DEV).requires_grad_(True), wp.to(DEV).requires_grad_(True)
+    gc = ops.colmean_sigmoid(zc) @ wc.t() + bp.to(DEV)
+    lc = losses.SingleBranchContrast(losses.JSD(), "G2L")(h=zc, g=gc, hn=znc)
+    lc.backward()
+    assert abs(float(lc) - float(ld)) <= 1e-4 * max(1.0, abs(float(ld)))
+    assert rel_err(zc.grad, zd.grad) < 1e-4 and rel_err(znc.grad, znd.grad) < 1e-4 and rel_err(wc.grad, wd.grad) < 1e-4
+    # GGD: (z W^T + b).sum(1) -> BCE
+    zd2, wd2, bd2 = z.double().requires_grad_(True), wp.double().requires_grad_(True), bp.double().requires_grad_(True)
+    l2 = pygcl.ggd_loss_as_written(zd2, zn.double(), wd2, bd2)
+    l2.backward()
+    zc2, wc2, bc2 = z.to(DEV).requires_grad_(True), wp.to(DEV).requires_grad_(True), bp.to(DEV).requires_grad_(True)
+    wv, bs = wc2.sum(0), bc2.sum()
+    l2c = losses.bce_with_logits_pos_neg(ops.rowdot(zc2, wv) + bs, ops.rowdot(zn.to(DEV), wv) + bs)
+    l2c.backward()
+    assert abs(float(l2c) - float(l2)) <= 1e-4 * max(1.0, abs(float(l2)))
+    assert rel_err(zc2.grad, zd2.grad) < 1e-4 and rel_err(wc2.grad, wd2.grad) < 1e-4 and rel_err(bc2.grad, bd2.grad) < 1e-4
+    # determinism: bitwise identical on re-run
+    l2c_b = losses.bce_with_logits_pos_neg(ops.rowdot(zc2, wv) + bs, ops.rowdot(zn.to(DEV), wv) + bs)
+    assert float(l2c_b) == float(l2c)
+
+
+@pytest.mark.parametrize("n,m,e", [(50, 3, 32), (200, 2, 768), (64, 1, 64), (33, 4, 256)])
+def test_attention_fusion(n, m, e, golden_dir):
+    from biomedkg_b200.utils.fusion import AttentionFusion
+
+    torch.manual_seed(n)
+    ref = om.AttentionFusion(e).double()
+    x = torch.randn(n, m, e, dtype=torch.float64)
+    x = x / x.norm(dim=1, keepdim=True)
+    go = torch.randn(n, e, dtype=torch.float64)
+    out = ref(x)
+    out.backward(go)
+    fus = AttentionFusion(e).to(DEV)
+    fus.load_state_dict(ref.state_dict())
+    oc = fus(x.float().to(DEV))
+    oc.backward(go.float().to(DEV))
+    assert rel_err(oc, out) < 1e-2
+    for k, p in fus.named_parameters():
+        assert rel_err(p.grad, dict(ref.named_parameters())[k].grad) < 2e-2, k
+
+
+def test_attention_fusion_reference_golden(golden_dir):
+    import os
+    from biomedkg_b200.utils.fusion import AttentionFusion, ReDAF
+
+    fx = torch.load(os.path.join(golden_dir, "fusion_attention_m3.pt"), weights_only=False)
+    fus = AttentionFusion(fx["x"].size(-1)).to(DEV)
+    fus.load_state_dict(fx["state_dict"])
+    assert rel_err(fus(fx["x"].float().to(DEV)), fx["out"]) < 1e-2
+    fx = torch.load(os.path.join(golden_dir, "fusion_redaf_m2.pt"), weights_only=False)
+    red = ReDAF(fx["x"].size(-1)).to(DEV).eval()
+    red.load_state_dict(fx["state_dict"])
+    assert rel_err(red(fx["x"].to(DEV)), fx["out"]) < 1e-2

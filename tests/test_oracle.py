@@ -1,0 +1,165 @@
+"""CPU tests of the oracle itself (no GPU): it must reproduce the golden vectors generated from the
+reference's own modules, its closed forms must equal the as-written PyG/PyGCL forms, and the
+canonical CSR must have the properties SURVEY.md App. A.8 states."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as om
+from oracle import pyg, pygcl
+
+MODULE_FIXTURES = ["grace_none", "grace_mean2", "grace_attention", "dgi_none", "ggd_none_a", "ggd_none_b", "ggd_redaf"]
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", MODULE_FIXTURES)
+def test_oracle_reproduces_reference_golden(golden_dir, name):
+    fx = _load(golden_dir, name)
+    cfg = fx["cfg"]
+    m = getattr(om, cfg["cls"])(cfg["in_dim"], cfg["hidden_dim"], cfg["out_dim"], cfg["num_hidden_layers"], fuse_method=cfg["fuse_method"])
+    m = m.to(fx["x"].dtype)
+    m.load_state_dict(fx["state_dict"])
+    m.train(name != "ggd_redaf")
+    om.set_draws(m, om.ReplayDraws(fx["draws"]))
+    loss = m.training_step(fx["x"], fx["edge_index"])
+    loss.backward()
+    tol = 1e-5 if fx["x"].dtype == torch.float32 else 1e-10
+    assert abs(float(loss) - float(fx["loss"])) <= tol * max(1.0, abs(float(fx["loss"])))
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(grads) == set(fx["grads"])
+    for k, g in grads.items():
+        assert torch.allclose(g, fx["grads"][k], rtol=tol * 10, atol=tol)
+    m.eval()
+    with torch.no_grad():
+        assert torch.allclose(m(fx["x"], fx["edge_index"]), fx["embed_eval"], rtol=tol * 10, atol=tol)
+
+
+def test_ggd_fixtures_cover_both_coin_branches(golden_dir):
+    coins = [[d[1] for d in _load(golden_dir, n)["draws"] if d[0] == "coin"][0] for n in ("ggd_none_a", "ggd_none_b")]
+    assert min(coins) < 0.5 <= max(coins)
+
+
+def test_fusion_goldens(golden_dir):
+    fx = _load(golden_dir, "fusion_attention_m3")
+    att = om.AttentionFusion(fx["x"].size(-1)).double()
+    att.load_state_dict(fx["state_dict"])
+    assert torch.allclose(att(fx["x"]), fx["out"], atol=1e-12)
+    fx = _load(golden_dir, "fusion_redaf_m2")
+    red = om.ReDAF(fx["x"].size(-1)).eval()
+    red.load_state_dict(fx["state_dict"])
+    assert torch.allclose(red(fx["x"]), fx["out"], atol=1e-6)
+
+
+def test_gcn_encoder_golden(golden_dir):
+    fx = _load(golden_dir, "gcn_encoder_eval")
+    enc = om.GCNEncoder(fx["x"].size(1), 64, 64, 2).double().eval()
+    enc.load_state_dict(fx["state_dict"])
+    with torch.no_grad():
+        assert torch.allclose(enc(fx["x"], fx["edge_index"]), fx["out"], atol=1e-12)
+
+
+# ---- hand-computable graphs: gcn_conv (gather/scatter form) vs dense A_hat --------------------------
+GRAPHS = {
+    "path": (4, [[0, 1, 1, 2, 2, 3], [1, 0, 2, 1, 3, 2]]),
+    "star": (5, [[1, 2, 3, 4], [0, 0, 0, 0]]),
+    "duplicates": (3, [[0, 0, 0, 1], [1, 1, 1, 2]]),
+    "self_loops": (3, [[0, 1, 1, 2], [0, 1, 2, 2]]),
+    "isolated": (4, [[0], [1]]),
+    "asymmetric": (4, [[0, 1, 2, 3, 3], [1, 2, 3, 0, 1]]),
+    "empty": (3, [[], []]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GRAPHS))
+def test_gcn_conv_matches_dense_formula(name):
+    n, e = GRAPHS[name]
+    ei = torch.tensor(e, dtype=torch.int64).reshape(2, -1)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 5, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 5, generator=g, dtype=torch.float64)
+    b = torch.randn(3, generator=g, dtype=torch.float64)
+    ref = pyg.gcn_dense_adj(ei, n) @ (x @ w.t()) + b
+    assert torch.allclose(pyg.gcn_conv(x, ei, w, b), ref, atol=1e-12)
+
+
+def test_star_values_by_hand():
+    # node 0 has in-degree 4+1, leaves have in-degree 1 (self-loop only); leaf->hub weight = 1/sqrt(5*1)
+    ei = torch.tensor(GRAPHS["star"][1])
+    _, w = pyg.gcn_norm(ei, 5, torch.float64)
+    assert torch.allclose(w[:4], torch.full((4,), 1 / math.sqrt(5.0), dtype=torch.float64))
+    assert torch.allclose(w[4:], torch.tensor([1 / 5.0, 1, 1, 1, 1], dtype=torch.float64))
+
+
+# ---- closed forms vs as-written ---------------------------------------------------------------------
+@pytest.mark.parametrize("n,d", [(7, 8), (64, 32), (130, 16)])
+def test_infonce_closed_form(n, d):
+    g = torch.Generator().manual_seed(n)
+    h1 = torch.randn(n, d, generator=g, dtype=torch.float64) * 3
+    h2 = torch.randn(n, d, generator=g, dtype=torch.float64)
+    a = pygcl.infonce_l2l_as_written(h1, h2, 0.2, True)
+    b = pygcl.infonce_l2l_closed_form(h1, h2, 0.2)
+    assert abs(float(a - b)) < 1e-11
+    # invariant to positive row scaling of h (normalisation)
+    c = pygcl.infonce_l2l_closed_form(h1 * torch.rand(n, 1, generator=g, dtype=torch.float64).add(0.1), h2, 0.2)
+    assert abs(float(a - c)) < 1e-11
+
+
+def test_jsd_and_ggd_closed_forms():
+    g = torch.Generator().manual_seed(3)
+    h, hn = torch.randn(50, 16, generator=g, dtype=torch.float64), torch.randn(50, 16, generator=g, dtype=torch.float64)
+    s = torch.randn(1, 16, generator=g, dtype=torch.float64)
+    assert abs(float(pygcl.jsd_g2l_as_written(h, s, hn) - pygcl.jsd_g2l_closed_form(h, s, hn))) < 1e-10
+    w, b = torch.randn(16, 16, generator=g, dtype=torch.float64), torch.randn(16, generator=g, dtype=torch.float64)
+    assert abs(float(pygcl.ggd_loss_as_written(h, hn, w, b) - pygcl.ggd_loss_closed_form(h, hn, w, b))) < 1e-10
+
+
+# ---- canonical CSR properties -------------------------------------------------------------------------
+def _rand_graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (2, e), generator=g, dtype=torch.int64)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_csr_invariant_to_edge_order_and_consistent(seed):
+    n, e = 23, 200
+    ei = pyg.view_graph(_rand_graph(n, e, seed), n)
+    rp, ci, perm = pyg.canonical_csr(ei, n)
+    g = torch.Generator().manual_seed(100 + seed)
+    shuffle = torch.randperm(ei.size(1), generator=g)
+    rp2, ci2, _ = pyg.canonical_csr(ei[:, shuffle], n)
+    assert torch.equal(rp, rp2) and torch.equal(ci, ci2)           # (rowptr, colind) unique per edge multiset
+    assert int(rp[-1]) == ei.size(1) and torch.equal(ei[0][perm.long()].int(), ci)
+    dst_sorted = ei[1][perm.long()]
+    assert bool((dst_sorted[1:] >= dst_sorted[:-1]).all())
+    rn, cn, pn = pyg.canonical_csr_numpy(ei.numpy(), n)
+    assert np.array_equal(rn, rp.numpy()) and np.array_equal(cn, ci.numpy()) and np.array_equal(pn, perm.numpy())
+    # CSC is the CSR of the transposed graph
+    rps, cis, _ = pyg.canonical_csr(ei, n, by="src")
+    rpt, cit, _ = pyg.canonical_csr(ei.flip(0), n, by="dst")
+    assert torch.equal(rps, rpt) and torch.equal(cis, cit)
+
+
+def test_gat_conv_matches_dense_softmax():
+    n = 6
+    ei = torch.tensor([[0, 1, 2, 3, 4, 4, 2], [1, 2, 0, 0, 0, 5, 2]])
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 4, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 4, generator=g, dtype=torch.float64)
+    a_s, a_d = torch.randn(1, 1, 3, generator=g, dtype=torch.float64), torch.randn(1, 1, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(3, generator=g, dtype=torch.float64)
+    out = pyg.gat_conv(x, ei, w, a_s, a_d, b)
+    xh = x @ w.t()
+    ei2 = pyg.add_remaining_self_loops(ei, n)
+    ref = torch.zeros(n, 3, dtype=torch.float64)
+    for i in range(n):
+        src = ei2[0][ei2[1] == i]
+        e = torch.nn.functional.leaky_relu((xh[src] * a_s.view(-1)).sum(-1) + (xh[i] * a_d.view(-1)).sum(), 0.2)
+        ref[i] = torch.softmax(e, 0) @ xh[src]
+    assert torch.allclose(out, ref + b, atol=1e-12)
