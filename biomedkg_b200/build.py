@@ -1,6 +1,6 @@
 """In-tree build of the sm_100a kernel library (nvcc cross-compiles without a GPU).
 
-    python -m biomedkg_b200.build [--force]
+    python biomedkg_b200/build.py [--force]      (run by path: importing the package needs the .so)
 
 Produces biomedkg_b200/_lib/libbmkg_b200.so: every .cu under csrc/ compiled with
 -gencode arch=compute_100a,code=sm_100a -lineinfo and linked with a static cudart,

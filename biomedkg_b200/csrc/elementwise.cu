@@ -110,12 +110,15 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int nb, 
   out[c] = s;
 }
 
-// column partial sums of a fp32 [N, C] matrix (optionally row-weighted), same CTA/row layout
+// column partial sums of a fp32 [N, C] matrix (optionally row-weighted), same CTA/row layout.
+// blockIdx.y selects a 1024-column slab so any C is covered.
 __global__ void __launch_bounds__(kEwThreads) colsum_partial_kernel(const float* __restrict__ z, const float* __restrict__ roww,
                                                                     int64_t N, int C, int rows_per_cta,
                                                                     float* __restrict__ partial) {
-  extern __shared__ float red[];
-  const int quad = C / 4;
+  __shared__ float red[1024];  // groups * cw <= 256 * 4
+  const int col0 = blockIdx.y * 1024;
+  const int cw = min(1024, C - col0);
+  const int quad = cw / 4;
   const int groups = kEwThreads / quad;
   const int g = threadIdx.x / quad, o = threadIdx.x % quad;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -123,17 +126,17 @@ __global__ void __launch_bounds__(kEwThreads) colsum_partial_kernel(const float*
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (g < groups) {
     for (int64_t r = r0 + g; r < r1; r += groups) {
-      const float4 v = reinterpret_cast<const float4*>(z + r * C)[o];
+      const float4 v = reinterpret_cast<const float4*>(z + r * C + col0)[o];
       const float w = roww ? roww[r] : 1.f;
       acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
     }
-    reinterpret_cast<float4*>(red + g * C)[o] = acc;
+    reinterpret_cast<float4*>(red + g * cw)[o] = acc;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+  for (int c = threadIdx.x; c < cw; c += kEwThreads) {
     float s = 0.f;
-    for (int gg = 0; gg < groups; ++gg) s += red[gg * C + c];
-    partial[(int64_t)blockIdx.x * C + c] = s;
+    for (int gg = 0; gg < groups; ++gg) s += red[gg * cw + c];
+    partial[(int64_t)blockIdx.x * C + col0 + c] = s;
   }
 }
 
@@ -201,6 +204,12 @@ using namespace bmkg;
 
 extern "C" {
 
+int bmkg_bind_device(int device) {
+  // The library links its own static cudart: bind that runtime (and the calling thread's driver context, which
+  // cuTensorMapEncodeTiled needs) to the caller's device.  Call once per host thread before the first launch.
+  return cudaSetDevice(device) == cudaSuccess ? BMKG_OK : BMKG_ERR_BAD_ARG;
+}
+
 int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, int64_t n, void* x0, void* x1, void* x2,
                    void* stream) {
   BMKG_REQUIRE(x && n >= 0 && n % 4 == 0, BMKG_ERR_BAD_ARG);
@@ -244,15 +253,14 @@ int bmkg_relu_dropout_bwd(const void* gy_bf16, const void* y_bf16, float scale, 
 }
 
 int bmkg_colsum(const float* z, const float* row_weight, int64_t N, int C, float* out, void* ws, size_t ws_bytes, void* stream) {
-  BMKG_REQUIRE(z && out && N > 0 && C % 4 == 0 && C >= 4 && C / 4 <= kEwThreads, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(z && out && N > 0 && C % 4 == 0 && C >= 4, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(ws && ws_bytes >= bmkg_colsum_workspace_bytes(N, C), BMKG_ERR_WORKSPACE);
   BMKG_REQUIRE(aligned16(z), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nb = colsum_ctas(N);
   const int rows_per_cta = (int)ceil_div(N, nb);
-  const int groups = kEwThreads / (C / 4);
-  colsum_partial_kernel<<<nb, kEwThreads, (size_t)groups * C * sizeof(float), st>>>(z, row_weight, N, C, rows_per_cta,
-                                                                                    static_cast<float*>(ws));
+  colsum_partial_kernel<<<dim3(nb, (unsigned)ceil_div(C, 1024)), kEwThreads, 0, st>>>(z, row_weight, N, C, rows_per_cta,
+                                                                                       static_cast<float*>(ws));
   colsum_finish_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), nb, C, out);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;

@@ -453,14 +453,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static int g_last_driver_status = 0;  // last CUresult / query status seen by the tensor-map path (diagnostics)
+
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      g_last_driver_status = 100000 + (int)e * 100 + (int)q;
   }
   return fn;
 }
@@ -476,6 +480,7 @@ static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D) 
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(z), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) g_last_driver_status = (int)r;
   return r == CUDA_SUCCESS ? BMKG_OK : BMKG_ERR_DRIVER;
 }
 
@@ -498,6 +503,8 @@ using namespace bmkg;
 using namespace bmkg::nce;
 
 extern "C" {
+
+int bmkg_last_driver_status(void) { return g_last_driver_status; }
 
 int64_t bmkg_infonce_padded_rows(int64_t N) { return ceil_div(2 * N, kBN) * kBN; }
 

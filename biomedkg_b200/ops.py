@@ -30,6 +30,12 @@ def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("biomedkg_b200 kernels are CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+    for t in ts:
+        if t is not None:
+            if t.device.index != torch.cuda.current_device():
+                raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}")
+            _cabi.bind_thread(t.device.index)
+            return
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -307,6 +313,7 @@ class _RowDotFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, v):
         _need_cuda(z, v)
+        ctx.v_shape = v.shape
         z, v = z.contiguous().float(), v.contiguous().float().view(-1)
         N, C = z.shape
         out = torch.empty(N, dtype=torch.float32, device=z.device)
@@ -324,7 +331,7 @@ class _RowDotFn(torch.autograd.Function):
             dz = torch.empty_like(z)
             call("bmkg_rowdot_bwd", _p(g), _p(v), N, C, _p(dz), _stream())
         if ctx.needs_input_grad[1]:
-            dv = colsum(z, g)
+            dv = colsum(z, g).view(ctx.v_shape)
         return dz, dv
 
 

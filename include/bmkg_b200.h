@@ -28,7 +28,12 @@ extern "C" {
 #define BMKG_ABI_VERSION 1
 
 int bmkg_abi_version(void);
+/* last CUresult (or 100000 + cudaError*100 + query status) seen while building a TMA tensor map; 0 = none */
+int bmkg_last_driver_status(void);
 const char* bmkg_error_string(int code);
+/* Bind the calling host thread to CUDA device `device` (the library carries its own static cudart; a thread that never
+ * touched CUDA - e.g. an autograd worker - has no current context and would otherwise default to device 0). */
+int bmkg_bind_device(int device);
 
 /* ---- G1: edge_index -> sorted parent graph ------------------------------------------
  * Replaces the per-call COO handling inside PyG GCNConv (biomedkg/model/encoder.py:155,160).

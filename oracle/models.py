@@ -155,6 +155,10 @@ class GCNEncoder(nn.Module):
         self.graph_layers = nn.ModuleList(layers)
         self.reset_parameters()
         self.draws = None  # None -> torch's own F.dropout
+        #: optional list of [N,C] bool masks consumed one per hidden layer: when set, the ReLU/dropout
+        #: decisions are taken from it (x = pre * mask * scale) instead of from the fp64 pre-activation.
+        #: Tests use it to compare gradients under the decisions a reduced-precision forward actually took.
+        self.relu_override = None
 
     def reset_parameters(self):
         for layer in self.graph_layers:
@@ -170,6 +174,15 @@ class GCNEncoder(nn.Module):
 
     def forward(self, x, edge_index):
         for layer in self.graph_layers[:-1]:
+            if self.relu_override is not None:
+                mask = self.relu_override.pop(0).to(x.dtype)
+                scale = 1.0
+                if self.drop_out and self.training:
+                    scale = 1.0 / (1.0 - 0.2)
+                    if self.draws is not None:
+                        self.draws.dropout_mask(x, 0.2)      # keep the draw order; the decision is in `mask`
+                x = layer(x, edge_index) * mask * scale
+                continue
             x = F.relu(layer(x, edge_index))
             if self.drop_out:
                 x = self._dropout(x)

@@ -12,9 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def libpath():
-    from biomedkg_b200.build import build_library
+    import __graft_entry__ as ge
 
-    return build_library()
+    return ge._load_build_module().build_library()
 
 
 def _declared():
@@ -25,7 +25,7 @@ def _declared():
 def test_library_exports_every_declared_symbol(libpath):
     lib = ctypes.CDLL(libpath)
     names = _declared()
-    assert len(names) >= 26
+    assert len(names) >= 28
     assert [n for n in names if not hasattr(lib, n)] == []
 
 

@@ -55,7 +55,7 @@ def test_infonce_full_size_cfg2_properties():
     n, d = 28_000, 256
     g = torch.Generator().manual_seed(1)
     h1 = torch.randn(n, d, generator=g).to(DEV).requires_grad_(True)
-    h2 = (h1.detach() + 0.7 * torch.randn(n, d, generator=g).to(DEV)).requires_grad_(True)
+    h2 = (h1.detach() + 2.0 * torch.randn(n, d, generator=g).to(DEV)).requires_grad_(True)
     loss = ops.infonce_loss(h1, h2, 0.2)
     loss.backward()
     # blockwise closed form in fp32 on the device (torch reference of the same op)

@@ -71,19 +71,25 @@ def test_gcn_layer_autograd_matches_oracle():
     b = torch.randn(c, generator=g) * 0.1
     keep = torch.rand(n, c, generator=g) >= 0.2
     gy = torch.randn(n, c, generator=g)
-    # oracle in fp64 on the same bf16-rounded inputs
-    xd = x.bfloat16().double().requires_grad_(True)
-    wd = w.double().requires_grad_(True)
-    bd = b.double().requires_grad_(True)
-    yd = torch.relu(pyg.gcn_conv(xd, ei, wd, bd)) * keep / 0.8
-    yd.backward(gy.double())
     view = ops.SortedGraph(ei.to(DEV), n).view(None)
     xc = x.bfloat16().to(DEV).requires_grad_(True)
     wc = w.to(DEV).requires_grad_(True)
     bc = b.to(DEV).requires_grad_(True)
     yc = ops.gcn_layer(xc, wc, bc, view, True, 0.2, 0, keep.to(DEV), False)
     yc.backward(gy.to(DEV).bfloat16())
-    assert rel_err(yc.float(), yd) < 1e-2
+    # oracle in fp64 on the same bf16-rounded inputs.  ReLU is a step function: a pre-activation that bf16 rounding
+    # moves across 0 flips a whole gradient term (a fraction f of flips costs ~sqrt(f) relative error, 2.5% here),
+    # so the backward is compared with the ReLU decisions the device actually took.
+    xd = x.bfloat16().double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    pre = pyg.gcn_conv(xd, ei, wd, bd)
+    yd_true = torch.relu(pre) * keep / 0.8
+    flips = ((pre > 0) & keep) != (yc.cpu() > 0)
+    assert float(flips.float().mean()) < 5e-3
+    yd = pre * (yc.cpu() > 0) / 0.8
+    yd.backward(gy.double())
+    assert rel_err(yc.float(), yd_true) < 1e-2
     assert rel_err(wc.grad, wd.grad) < 1e-2
     assert rel_err(bc.grad, bd.grad) < 1e-2
     assert rel_err(xc.grad.float(), xd.grad) < 1e-2
@@ -152,8 +158,12 @@ def test_attention_fusion(n, m, e, golden_dir):
     oc = fus(x.float().to(DEV))
     oc.backward(go.float().to(DEV))
     assert rel_err(oc, out) < 1e-2
+    refp = dict(ref.named_parameters())
     for k, p in fus.named_parameters():
-        assert rel_err(p.grad, dict(ref.named_parameters())[k].grad) < 2e-2, k
+        if k == "k_proj.bias":   # softmax is invariant to a shift of all keys: the true gradient is exactly 0
+            assert float(p.grad.norm()) < 2e-2 * float(refp["q_proj.bias"].grad.norm()) + 1e-6
+        else:
+            assert rel_err(p.grad, refp[k].grad) < 2e-2, k
 
 
 def test_attention_fusion_reference_golden(golden_dir):
