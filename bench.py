@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py - GCL nodes/s of one full-graph GRACE training step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+
+A "step" = fusion + 3 encoder passes + projector + InfoNCE + backward + grad all-reduce (N>1) + grad clip + Adam,
+exactly BaseGCL.training_step + the Lightning optimiser step of the reference (gcl_module.py:60-64,
+train_gcl.py:99).  N=1 workload: BASELINE.json configs[1] (GRACE + GAT + attention fusion of 2 modalities,
+~28k nodes / ~650k edges).  N>1: every rank runs its own subgraph of that shape (the reference's DDP regime:
+per-rank contrast, gradients all-reduced over NCCL) -> weak scaling, value = total nodes / max-over-ranks time.
+
+Prints ONE JSON line (see the driver contract in DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (N, E, M, fuse, encoder, objective)  - BASELINE.json configs, SURVEY.md section 8 table
+    "cfg1": dict(N=8_000, E=2_670_000, M=1, fuse="none", encoder="gcn", desc="GRACE + 2-layer-hidden GCN, drug subgraph"),
+    "cfg2": dict(N=28_000, E=650_000, M=2, fuse="attention", encoder="gat", desc="GRACE + GAT + attention fusion (2 modalities), gene/protein subgraph"),
+    "cfg4": dict(N=130_000, E=8_000_000, M=3, fuse="attention", encoder="gcn", desc="PrimeKG++-scale full graph, 3-modality fusion, GRACE"),
+}
+IN_DIM, HID, LAYERS, TAU = 768, 256, 2, 0.2
+
+
+def synth(cfg, seed, pin=False):
+    """Synthetic inputs of the named shape: LM-like features normalised over the modality axis
+    (data/node.py:115-117), Erdos-Renyi-like int64 edge_index with duplicates and self-loops left in."""
+    g = torch.Generator().manual_seed(seed)
+    N, E, M = cfg["N"], cfg["E"], cfg["M"]
+    if M > 1:
+        x = torch.randn(N, M, IN_DIM, generator=g)
+        x = x / x.norm(dim=1, keepdim=True)
+    else:
+        x = torch.nn.init.xavier_normal_(torch.empty(N, IN_DIM), generator=g)
+    ei = torch.randint(0, N, (2, E), generator=g, dtype=torch.int64)
+    if pin:
+        x, ei = x.pin_memory(), ei.pin_memory()
+    return x, ei
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples that arrived inside [t0, t1] (the timed region)."""
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for ts, r in self.rows if len(r) >= 9 and (t0 is None or t0 <= ts <= t1 + 0.15)]
+        sm = sorted(int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit())
+        mx = max((int(float(r[2])) for r in rows if r[2].replace(".", "").isdigit()), default=None)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the restated PyG/PyGCL path ("as written"), timed on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(cfg, n_sample, steps, warmup, seed=42):
+    """nodes/s of the oracle's as-written GRACE step (COO gather + scatter_add_, mask-materialising [N,2N] InfoNCE -
+    the operations PyG 2.5.3 / PyGCL 0.1.2 execute) on a bounded sample: an n_sample-node graph of the same shape
+    (same average degree, modalities, encoder, objective).  fp32, all host threads."""
+    from oracle import models as om
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sub = dict(cfg)
+    sub["N"] = n_sample
+    sub["E"] = max(1, int(cfg["E"] * n_sample / cfg["N"]))
+    x, ei = synth(sub, seed)
+    torch.manual_seed(seed)
+    mod = om.GRACEModule(IN_DIM, HID, HID, LAYERS, fuse_method=cfg["fuse"], encoder=cfg["encoder"]).train()
+    opt = torch.optim.Adam(mod.model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(x, ei)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(mod.model.parameters(), 1.0)
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_sample / dt, dt, sub
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    n_sample = args.cpu_sample_nodes
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, dt, sub = cpu_reference_step_rate(cfg, n_sample, steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = (f"restated reference path (PyG/PyGCL not installable): oracle as-written GRACE step on a {sub['N']}-node / "
+              f"{sub['E']}-edge sample of {args.config} (same degree, M={cfg['M']}, fuse={cfg['fuse']}, encoder={cfg['encoder']}), "
+              f"fp32, {steps} steps")
+    line = {
+        "impl": "reference", "metric": "GCL nodes/sec", "value": rate, "unit": "nodes/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.config}: {cfg['desc']}", "sample_nodes": sub["N"], "sample_edges": sub["E"]},
+        "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import biomedkg_b200 as b
+    from biomedkg_b200 import _cabi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = CONFIGS[args.config]
+    N, E, M = cfg["N"], cfg["E"], cfg["M"]
+    x_host, ei_host = synth(cfg, 42 + rank, pin=True)
+    torch.manual_seed(42)
+    mod = b.GRACEModule(IN_DIM, HID, HID, LAYERS, scheduler_type="cosine", learning_rate=1e-3, warm_up_ratio=0.2,
+                        fuse_method=cfg["fuse"], encoder=cfg["encoder"]).to(dev).train()
+    params = [p for p in mod.model.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-3)
+
+    class Batch:
+        pass
+
+    def step(batch):
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(batch)
+        loss.backward()
+        if world > 1:  # DDP-equivalent: average parameter gradients over ranks (NCCL all-reduce, ~2 MB)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)   # gradient_clip_val=1.0 (train_gcl.py:99)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # started before warm-up so it is already streaming in the timed region
+    res = Batch()
+    res.x, res.edge_index = x_host.to(dev), ei_host.to(dev)
+    for _ in range(args.warmup):
+        step(res)
+    barrier()
+    _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_gcn_aggregate", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+    _cabi.timings.clear()
+    launches0 = _cabi.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(res)
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_cabi.kernel_launches - launches0) // args.steps
+    kern_ms = {k: sum(a.elapsed_time(bb) for a, bb in v) / len(v) for k, v in _cabi.timings.items()}
+    kern_calls = {k: len(v) // args.steps for k, v in _cabi.timings.items()}
+    _cabi.timed_entries.clear()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = N * world / (ms_max * 1e-3)
+    final_loss = float(loss.detach())
+
+    # ---------------- end to end: host batch -> loss on host ----------------
+    def e2e_step():
+        bt = Batch()
+        bt.x = x_host.to(dev, non_blocking=True)
+        bt.edge_index = ei_host.to(dev, non_blocking=True)     # a fresh edge_index: the radix sort runs every step
+        return float(step(bt).item())                           # device -> host read of the loss
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    k2 = max(1, args.steps // 2)
+    e0.record()
+    for _ in range(k2):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / k2], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": N * world / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
+
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    if rank != 0:
+        return
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+    D = HID
+    flops_bwd, flops_fwd = 8.0 * N * N * D, 6.0 * N * N * D
+    roof = None
+    if "bmkg_infonce_bwd" in kern_ms:
+        ach = flops_bwd / (kern_ms["bmkg_infonce_bwd"] * 1e-3) / 1e12
+        roof = {"kernel": "infonce_bwd_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "traffic": None, "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": kern_ms["bmkg_infonce_bwd"],
+                "peak_source": peak_src,
+                "also": {"infonce_fwd (3 kernels, 6N^2D)": {"ms": kern_ms.get("bmkg_infonce_fwd"),
+                                                         "achieved_tflops": flops_fwd / (kern_ms["bmkg_infonce_fwd"] * 1e-3) / 1e12}}}
+        agg_key = "bmkg_gat_aggregate" if cfg["encoder"] == "gat" else "bmkg_gcn_aggregate"
+        if agg_key in kern_ms:
+            roof["also"][agg_key] = {"ms_avg_per_call": kern_ms[agg_key], "calls_per_step": kern_calls[agg_key]}
+        if "bmkg_gat_aggregate_bwd" in kern_ms:
+            roof["also"]["bmkg_gat_aggregate_bwd"] = {"ms_avg_per_call": kern_ms["bmkg_gat_aggregate_bwd"], "calls_per_step": kern_calls["bmkg_gat_aggregate_bwd"]}
+
+    # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, sub = cpu_reference_step_rate(cfg, args.cpu_sample_nodes, 2, 1)
+        cpu = {"value": rate, "unit": "nodes/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"oracle as-written GRACE step (restated PyG/PyGCL path), {sub['N']}-node / {sub['E']}-edge sample of {args.config}, fp32, 2 steps, {dt:.2f} s/step"}
+
+    line = {
+        "metric": "GCL nodes/sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "nodes_per_gpu": N, "edges_per_gpu": E, "modalities": M, "in_dim": IN_DIM,
+                   "hidden": HID, "conv_layers": LAYERS + 2, "tau": TAU, "parallelism": f"dp{world} (per-rank graph, NCCL grad all-reduce)",
+                   "l2_policy": "inputs larger than L2 (x is %.0f MB fp32); no explicit flush" % (x_host.numel() * 4 / 1e6),
+                   "unused_view": "computed (faithful to model/gcl.py:44)"},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-sample-nodes", type=int, default=6000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,9 @@ SIGNATURES = {
     "bmkg_csr_filter_workspace_bytes": (SZ, [I64, I64]),
     "bmkg_csr_filter": (I, [P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, SZ, P]),
     "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, P]),
+    "bmkg_gat_scores": (I, [P, P, P, I64, I, I, P, P, P]),
+    "bmkg_gat_aggregate": (I, [P, P, P, P, P, I64, I, I, F, P, I, F, U64, P, P, I, P, P, P]),
+    "bmkg_gat_aggregate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, F, P, P, P, P, P]),
     "bmkg_mask_cast": (I, [P, P, P, I64, P, P, P, P]),
     "bmkg_modality_mean": (I, [P, I64, I, I, P, P, P]),
     "bmkg_colsum_workspace_bytes": (SZ, [I64, I]),
@@ -93,9 +96,33 @@ def bind_thread(device_index: int) -> None:
         _tls.device = device_index
 
 
+#: CUDA kernels each entry point launches per call (for bench.py's gpu_launches count)
+KERNELS_PER_CALL = {
+    "bmkg_edge_sort": None,            # data dependent: 3 + 5 * passes + 2 (counted by formula in bench.py)
+    "bmkg_csr_filter": 5, "bmkg_gcn_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
+    "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
+    "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
+    "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
+    "bmkg_infonce_bwd": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2,
+}
+kernel_launches = 0
+
+#: optional per-entry-point device timing (bench.py): name -> list of (start_event, end_event) on the launch stream
+timed_entries: set = set()
+timings: dict = {}
+
+
 def call(name: str, *args) -> None:
     """Launch one C-ABI entry point on the calling thread's current torch device."""
-    global call_count
+    global call_count, kernel_launches
     call_count += 1
+    kernel_launches += KERNELS_PER_CALL.get(name) or 12
     bind_thread(torch.cuda.current_device())
+    if name in timed_entries:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib, name)(*args), name)
+        e1.record()
+        timings.setdefault(name, []).append((e0, e1))
+        return
     check(getattr(lib, name)(*args), name)

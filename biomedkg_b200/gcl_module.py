@@ -14,7 +14,7 @@ import torch
 from . import losses as L
 from .factory import FusionFactory
 from .losses import DualBranchContrast, SingleBranchContrast
-from .model import GCNEncoder
+from .model import GATEncoder, GCNEncoder
 from .model.gcl import DGI, GGD, GRACE
 from . import ops
 
@@ -118,6 +118,15 @@ class BaseGCL(LightningModule):
             return _cosine_with_warmup(optimizer, warm, num_training_steps)
 
 
+def _make_encoder(kind, in_dim, hidden_dim, out_dim, num_hidden_layers):
+    """kind="gcn" is the reference's encoder (gcl_module.py:118,161,208); "gat" is the BASELINE.json extension."""
+    if kind == "gcn":
+        return GCNEncoder(in_dim=in_dim, hidden_dim=hidden_dim, out_dim=out_dim, num_hidden_layers=num_hidden_layers)
+    if kind == "gat":
+        return GATEncoder(in_dim=in_dim, hidden_dim=hidden_dim, out_dim=out_dim, num_hidden_layers=num_hidden_layers)
+    raise ValueError(f"unknown encoder {kind!r}")
+
+
 def _common(self_cls, model, in_dim, scheduler_type, learning_rate, warm_up_ratio, fuse_method, contrast_model=None):
     return dict(model=model, embed_dim=in_dim, scheduler_type=scheduler_type, learning_rate=learning_rate,
                 warm_up_ratio=warm_up_ratio, feature_embedding_dim=in_dim, contrast_model=contrast_model,
@@ -128,8 +137,8 @@ class DGIModule(BaseGCL):
     """gcl_module.py:103-143."""
 
     def __init__(self, in_dim, hidden_dim, out_dim, num_hidden_layers, scheduler_type="cosine", learning_rate=2e-4,
-                 warm_up_ratio=0.03, fuse_method=None):
-        model = DGI(encoder=GCNEncoder(in_dim=in_dim, hidden_dim=hidden_dim, out_dim=out_dim, num_hidden_layers=num_hidden_layers),
+                 warm_up_ratio=0.03, fuse_method=None, encoder="gcn"):
+        model = DGI(encoder=_make_encoder(encoder, in_dim, hidden_dim, out_dim, num_hidden_layers),
                     hidden_dim=hidden_dim)
         contrast_model = SingleBranchContrast(loss=L.JSD(), mode="G2L")
         BaseGCL.__init__(self, **_common(self, model, in_dim, scheduler_type, learning_rate, warm_up_ratio, fuse_method, contrast_model))
@@ -143,8 +152,8 @@ class GRACEModule(BaseGCL):
     """gcl_module.py:146-190."""
 
     def __init__(self, in_dim, hidden_dim, out_dim, num_hidden_layers, scheduler_type="cosine", learning_rate=2e-4,
-                 warm_up_ratio=0.03, fuse_method=None):
-        model = GRACE(encoder=GCNEncoder(in_dim=in_dim, hidden_dim=hidden_dim, out_dim=out_dim, num_hidden_layers=num_hidden_layers),
+                 warm_up_ratio=0.03, fuse_method=None, encoder="gcn"):
+        model = GRACE(encoder=_make_encoder(encoder, in_dim, hidden_dim, out_dim, num_hidden_layers),
                       hidden_dim=hidden_dim, proj_dim=hidden_dim)
         contrast_model = DualBranchContrast(loss=L.InfoNCE(tau=0.2), mode="L2L", intraview_negs=True)
         BaseGCL.__init__(self, **_common(self, model, in_dim, scheduler_type, learning_rate, warm_up_ratio, fuse_method, contrast_model))
@@ -159,8 +168,8 @@ class GGDModule(BaseGCL):
     """gcl_module.py:193-234."""
 
     def __init__(self, in_dim, hidden_dim, out_dim, num_hidden_layers, scheduler_type="cosine", learning_rate=2e-4,
-                 warm_up_ratio=0.03, fuse_method=None):
-        model = GGD(encoder=GCNEncoder(in_dim=in_dim, hidden_dim=hidden_dim, out_dim=out_dim, num_hidden_layers=num_hidden_layers),
+                 warm_up_ratio=0.03, fuse_method=None, encoder="gcn"):
+        model = GGD(encoder=_make_encoder(encoder, in_dim, hidden_dim, out_dim, num_hidden_layers),
                     hidden_dim=hidden_dim, n_proj=1, aug_p=0.5)
         BaseGCL.__init__(self, **_common(self, model, in_dim, scheduler_type, learning_rate, warm_up_ratio, fuse_method))
 

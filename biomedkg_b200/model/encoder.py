@@ -51,14 +51,46 @@ class GCNConv(nn.Module):
         return ops.gcn_layer(x, self.lin.weight, self.bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32)
 
 
+class GATConv(nn.Module):
+    """Extension (BASELINE.json configs 2, 5): PyG GATConv(in, out, heads, concat=True, negative_slope=0.2,
+    add_self_loops=True) parameter layout - lin.weight [H*out, in], att_src/att_dst [1,H,out] glorot, bias [H*out]."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, negative_slope: float = 0.2):
+        super().__init__()
+        if heads not in (1, 2, 4) or out_channels % 8 or heads * out_channels > 1024:
+            raise ValueError("GATConv kernels support heads in {1,2,4}, out_channels % 8 == 0, heads*out_channels <= 1024")
+        self.in_channels, self.out_channels, self.heads, self.negative_slope = in_channels, out_channels, heads, negative_slope
+        self.lin = _Lin(in_channels, heads * out_channels)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _glorot_(self.lin.weight)
+        _glorot_(self.att_src)
+        _glorot_(self.att_dst)
+        with torch.no_grad():
+            self.bias.zero_()
+
+    def forward(self, x, edge_index, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=True):
+        view = ops.as_view(edge_index, x.size(0))
+        if x.dtype != ops.BF16:
+            x = ops.mask_cast(x.float())[0]
+        return ops.gat_layer(x, self.lin.weight, self.att_src, self.att_dst, self.bias, view, self.heads, self.negative_slope,
+                             relu, drop_p, drop_seed, drop_keep, out_fp32)
+
+
 class GCNEncoder(nn.Module):
-    def __init__(self, in_dim: int, hidden_dim: int, out_dim: int, num_hidden_layers: int, drop_out: bool = True):
+    conv_cls = GCNConv
+
+    def __init__(self, in_dim: int, hidden_dim: int, out_dim: int, num_hidden_layers: int, drop_out: bool = True, **conv_kw):
         super().__init__()
         self.drop_out = drop_out
-        layers = [GCNConv(in_dim, hidden_dim)]
+        layers = [self.conv_cls(in_dim, hidden_dim, **conv_kw)]
         for _ in range(num_hidden_layers):
-            layers.append(GCNConv(hidden_dim, hidden_dim))
-        layers.append(GCNConv(hidden_dim, out_dim))
+            layers.append(self.conv_cls(hidden_dim, hidden_dim, **conv_kw))
+        layers.append(self.conv_cls(hidden_dim, out_dim, **conv_kw))
         self.graph_layers = nn.ModuleList(layers)
         self.draws = DeviceDraws()
         self.reset_parameters()
@@ -79,3 +111,9 @@ class GCNEncoder(nn.Module):
                 seed, keep = self.draws.dropout((x.size(0), layer.out_channels), p, x.device)
             x = layer(x, view, relu=True, drop_p=p, drop_seed=seed, drop_keep=keep, out_fp32=False)
         return self.graph_layers[-1](x, view, relu=False, out_fp32=True)
+
+
+class GATEncoder(GCNEncoder):
+    """Extension: the GCNEncoder layer pattern (encoder.py:124-162) over GATConv; same forward(x, edge_index)."""
+
+    conv_cls = GATConv

@@ -307,6 +307,80 @@ def gcn_layer(x, weight, bias, view, relu, drop_p=0.0, drop_seed=0, drop_keep=No
 
 
 # ---------------------------------------------------------------------------
+# GAT layer (extension)
+# ---------------------------------------------------------------------------
+class _GATLayerFn(torch.autograd.Function):
+    """One GATConv (+ReLU+dropout): X W^T (library GEMM), node scores, fused warp-softmax aggregation.
+    Backward recomputes alpha from node arrays: a CSR pass (d a_dst, t) and a CSC pass (d xh, d a_src)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32):
+        _need_cuda(x)
+        assert x.dtype == BF16
+        x = x.contiguous()
+        N = x.size(0)
+        HC = weight.size(0)
+        C = HC // heads
+        dev = x.device
+        w16 = weight.to(BF16)
+        xh = torch.mm(x, w16.t())
+        atts = att_src.detach().reshape(-1).float().contiguous()
+        attd = att_dst.detach().reshape(-1).float().contiguous()
+        a_s = torch.empty(N, heads, dtype=torch.float32, device=dev)
+        a_d = torch.empty(N, heads, dtype=torch.float32, device=dev)
+        call("bmkg_gat_scores", _p(xh), _p(atts), _p(attd), N, heads, C, _p(a_s), _p(a_d), _stream())
+        out = torch.empty(N, HC, dtype=torch.float32 if out_fp32 else BF16, device=dev)
+        rmax = torch.empty(N, heads, dtype=torch.float32, device=dev)
+        rsum = torch.empty(N, heads, dtype=torch.float32, device=dev)
+        keep = _as_u8(drop_keep)
+        b = bias.detach().contiguous()
+        call("bmkg_gat_aggregate", _p(view.rowptr), _p(view.colind), _p(xh), _p(a_s), _p(a_d), N, heads, C, float(slope), _p(b),
+             int(relu), float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(keep), _p(out), int(out_fp32), _p(rmax), _p(rsum),
+             _stream())
+        ctx.view, ctx.relu, ctx.drop_p, ctx.heads, ctx.slope = view, relu, drop_p, heads, slope
+        ctx.att_shape = att_src.shape
+        ctx.save_for_backward(x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, y = ctx.saved_tensors
+        view, H = ctx.view, ctx.heads
+        gy = gy.contiguous()
+        N, HC = gy.shape
+        C = HC // H
+        dev = gy.device
+        if ctx.relu:
+            gy16 = gy if gy.dtype == BF16 else gy.to(BF16)
+            gpre = torch.empty(N, HC, dtype=BF16, device=dev)
+            dbias = torch.empty(HC, dtype=torch.float32, device=dev)
+            ws = _ws(lib.bmkg_colsum_workspace_bytes(N, HC), dev)
+            scale = 1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0 else 1.0
+            call("bmkg_relu_dropout_bwd", _p(gy16), _p(y), float(scale), N, HC, _p(gpre), _p(dbias), _p(ws), ws.numel(), _stream())
+        else:
+            dbias = colsum(gy.float())
+            gpre = gy if gy.dtype == BF16 else gy.to(BF16)
+        dxh = torch.empty(N, HC, dtype=BF16, device=dev)
+        das = torch.empty(N, H, dtype=torch.float32, device=dev)
+        dad = torch.empty(N, H, dtype=torch.float32, device=dev)
+        tsum = torch.empty(N, H, dtype=torch.float32, device=dev)
+        call("bmkg_gat_aggregate_bwd", _p(view.rowptr), _p(view.colind), _p(view.csc_rowptr), _p(view.csc_colind), _p(xh), _p(gpre),
+             _p(a_s), _p(a_d), _p(rmax), _p(rsum), _p(atts), _p(attd), N, H, C, float(ctx.slope), _p(dxh), _p(das), _p(dad),
+             _p(tsum), _stream())
+        xh3 = xh.view(N, H, C).float()
+        datt_s = torch.einsum("nh,nhc->hc", das, xh3).reshape(ctx.att_shape)
+        datt_d = torch.einsum("nh,nhc->hc", dad, xh3).reshape(ctx.att_shape)
+        dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None
+        dx = torch.mm(dxh, w16) if ctx.needs_input_grad[0] else None
+        return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None
+
+
+def gat_layer(x, weight, att_src, att_dst, bias, view, heads=1, slope=0.2, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None,
+              out_fp32=False):
+    return _GATLayerFn.apply(x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32)
+
+
+# ---------------------------------------------------------------------------
 # heads
 # ---------------------------------------------------------------------------
 class _RowDotFn(torch.autograd.Function):

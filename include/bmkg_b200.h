@@ -69,6 +69,24 @@ int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float
                        int channels, const float* bias, int relu, float drop_p, uint64_t drop_seed, const uint8_t* drop_keep,
                        void* out, int out_is_fp32, void* stream);
 
+/* ---- A3/A4: GAT aggregation (extension - BASELINE.json configs 2 and 5) ---------------------------
+ * PyG GATConv(in, out, heads=H, concat=True, negative_slope, add_self_loops=True) semantics;
+ * no reference call site on the GCL path (nearest: RGAT, biomedkg/model/encoder.py:62-121).
+ * xh bf16 [N, H*C] = x W^T; a_src/a_dst fp32 [N,H]; H in {1,2,4}, C % 8 == 0, H*C <= 1024.
+ * bmkg_gat_aggregate also writes rowmax/rowsum [N,H] (softmax statistics) for the backward, which recomputes
+ * alpha from node arrays: csr pass -> d_adst, tsum_ws [N,H]; csc pass -> dxh bf16 [N,H*C], d_asrc. */
+int bmkg_gat_scores(const void* xh_bf16, const float* att_src, const float* att_dst, int64_t num_nodes, int heads, int channels,
+                    float* a_src, float* a_dst, void* stream);
+int bmkg_gat_aggregate(const int32_t* rowptr, const int32_t* colind, const void* xh_bf16, const float* a_src, const float* a_dst,
+                       int64_t num_nodes, int heads, int channels, float negative_slope, const float* bias, int relu,
+                       float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, void* out, int out_is_fp32, float* rowmax,
+                       float* rowsum, void* stream);
+int bmkg_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* colind, const int32_t* csc_rowptr, const int32_t* csc_colind,
+                           const void* xh_bf16, const void* g_bf16, const float* a_src, const float* a_dst, const float* rowmax,
+                           const float* rowsum, const float* att_src, const float* att_dst, int64_t num_nodes, int heads,
+                           int channels, float negative_slope, void* dxh_bf16, float* d_asrc, float* d_adst, float* tsum_ws,
+                           void* stream);
+
 /* ---- elementwise / small reductions -------------------------------------------------------
  * bmkg_mask_cast: torch_geometric.utils.mask_feature(mode="all") (model/gcl.py:40-41,75) fused with the
  *   fp32->bf16 cast: x fp32 [n] -> x0 (plain), x1 (keep1), x2 (keep2), any of them NULL; n % 4 == 0.

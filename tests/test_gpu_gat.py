@@ -1,0 +1,105 @@
+"""A3/A4 parity (extension): fused GAT aggregation fwd/bwd vs the PyG GATConv restatement (oracle/pyg.py:gat_conv)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import models as om
+from oracle import pyg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _graph(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g, dtype=torch.int64)
+    if e > 8:
+        ei[1, :3] = ei[0, :3]
+        ei[:, -3:] = ei[:, :3]
+    return ei
+
+
+@pytest.mark.parametrize("n,e,cin,c,heads", [(60, 400, 32, 64, 1), (300, 5000, 96, 256, 1), (200, 3000, 64, 64, 4), (150, 0, 32, 128, 2),
+                                             (500, 9000, 128, 512, 2)])
+def test_gat_layer_forward_backward(n, e, cin, c, heads):
+    from biomedkg_b200 import ops
+
+    ei = _graph(n, e, n + e)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, cin, generator=g)
+    w = torch.randn(heads * c, cin, generator=g) * 0.2
+    a_s, a_d = torch.randn(1, heads, c, generator=g) * 0.3, torch.randn(1, heads, c, generator=g) * 0.3
+    b = torch.randn(heads * c, generator=g) * 0.1
+    gy = torch.randn(n, heads * c, generator=g)
+
+    # the oracle sees the same bf16-rounded x, W and xh = bf16(x W^T) the kernels aggregate
+    xd = x.bfloat16().double().requires_grad_(True)
+    wd = w.bfloat16().double().requires_grad_(True)
+    asd, add_, bd = a_s.double().requires_grad_(True), a_d.double().requires_grad_(True), b.double().requires_grad_(True)
+    yd = pyg.gat_conv(xd, ei, wd, asd, add_, bd, heads=heads)
+    yd.backward(gy.double())
+
+    view = ops.SortedGraph(ei.to(DEV), n).view(None)
+    xc = x.bfloat16().to(DEV).requires_grad_(True)
+    wc, asc, adc, bc = [t.to(DEV).requires_grad_(True) for t in (w, a_s, a_d, b)]
+    yc = ops.gat_layer(xc, wc, asc, adc, bc, view, heads=heads, relu=False, out_fp32=True)
+    yc.backward(gy.to(DEV))
+    assert rel_err(yc, yd) < 1e-2
+    assert rel_err(wc.grad, wd.grad) < 2e-2
+    assert rel_err(bc.grad, bd.grad) < 1e-2
+    if e == 0:   # self-loops only: alpha == 1 whatever the attention vectors are -> exactly zero gradient
+        assert float(asc.grad.abs().max()) < 1e-4 and float(adc.grad.abs().max()) < 1e-4
+    else:
+        assert rel_err(asc.grad, asd.grad) < 2e-2 and rel_err(adc.grad, add_.grad) < 2e-2
+    assert rel_err(xc.grad.float(), xd.grad) < 2e-2
+
+
+def test_gat_encoder_matches_oracle_eval_and_train():
+    import biomedkg_b200 as b
+    from biomedkg_b200.draws import ReplayDraws, set_draws
+
+    torch.manual_seed(4)
+    n, e = 400, 6000
+    ei = _graph(n, e, 9)
+    x = torch.randn(n, 64)
+    ref = om.GATEncoder(64, 256, 256, 2).double()
+    enc = b.model.GATEncoder(64, 256, 256, 2)
+    enc.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    enc = enc.to(DEV)
+    ref.eval(), enc.eval()
+    with torch.no_grad():
+        assert rel_err(enc(x.to(DEV), ei.to(DEV)), ref(x.double(), ei)) < 1e-2
+    # train mode with replayed dropout masks
+    ref.train(), enc.train()
+    draws = om.TorchDraws(record=True)
+    ref.draws = draws
+    out_ref = ref(x.double(), ei)
+    enc.draws = ReplayDraws(draws.log, DEV)
+    out = enc(x.to(DEV), ei.to(DEV))
+    assert rel_err(out, out_ref) < 1.5e-2
+
+
+def test_grace_gat_step_trains():
+    import biomedkg_b200 as b
+
+    torch.manual_seed(0)
+    n, e = 2000, 30_000
+    x = torch.randn(n, 2, 128)
+    x = (x / x.norm(dim=1, keepdim=True)).to(DEV)
+    ei = torch.randint(0, n, (2, e), dtype=torch.int64).to(DEV)
+    mod = b.GRACEModule(128, 256, 256, 2, fuse_method="attention", encoder="gat").to(DEV).train()
+    opt = torch.optim.Adam(mod.model.parameters(), lr=1e-3)
+
+    class Batch:
+        pass
+
+    Batch.x, Batch.edge_index = x, ei
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(Batch)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    assert all(p.grad is not None for p in mod.modality_transform.parameters())   # fuser grads populated, never optimised

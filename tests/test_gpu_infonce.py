@@ -27,7 +27,8 @@ def test_infonce_forward_backward(n, d):
     loss = ops.infonce_loss(x, y, 0.2)
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(ref)) <= 1e-3 * abs(float(ref)), (float(loss), float(ref))
+    # tiny N gives a tiny loss (log of a handful of terms): compare on the O(1) scale of its two terms
+    assert abs(float(loss) - float(ref)) <= 1e-3 * max(abs(float(ref)), 1.0), (float(loss), float(ref))
     assert rel_err(x.grad, a.grad) < 1e-2, rel_err(x.grad, a.grad)
     assert rel_err(y.grad, b.grad) < 1e-2, rel_err(y.grad, b.grad)
 
