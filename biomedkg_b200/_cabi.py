@@ -60,8 +60,10 @@ SIGNATURES = {
     "bmkg_softplus_pair_workspace_bytes": (SZ, [I64]),
     "bmkg_softplus_pair_sum": (I, [P, P, I64, P, P, SZ, P]),
     "bmkg_softplus_pair_bwd": (I, [P, P, P, I64, P, P, P]),
-    "bmkg_fusion_attn_fwd": (I, [P, I64, I, I, P, P, P]),
-    "bmkg_fusion_attn_bwd": (I, [P, P, P, I64, I, I, P, P]),
+    "bmkg_fusion_attn_fwd": (I, [P, P, I64, I, I, P, P, P]),
+    "bmkg_fusion_attn_bwd": (I, [P, P, P, P, I64, I, I, P, P]),
+    "bmkg_mask_cast_bwd": (I, [P, P, P, P, P, I64, P, P]),
+    "bmkg_colsum_bf16": (I, [P, P, P, I64, I, I, P, P, P, SZ, P]),
     "bmkg_infonce_padded_rows": (I64, [I64]),
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
     "bmkg_infonce_fwd": (I, [P, I64, I, P, P, P, SZ, P]),
@@ -103,7 +105,7 @@ KERNELS_PER_CALL = {
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
-    "bmkg_infonce_bwd": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2,
+    "bmkg_infonce_bwd": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
 }
 kernel_launches = 0
 

@@ -101,13 +101,22 @@ __global__ void __launch_bounds__(kEwThreads) relu_dropout_bwd_kernel(const __nv
   }
 }
 
-// out[c] = sum_b partial[b, c] in fixed order
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out[c] = sum_b partial[b, c]: 32 columns x 8 interleaved row groups per CTA, fixed-order combine (deterministic)
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int nb, int stride, int C, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * C + c];
-  out[c] = s;
+  if (c < C)
+    for (int b = g; b < nb; b += 8) s += partial[(int64_t)b * stride + c];
+  red[g][cl] = s;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cl];
+    out[c] = t;
+  }
 }
 
 // column partial sums of a fp32 [N, C] matrix (optionally row-weighted), same CTA/row layout.
@@ -137,6 +146,70 @@ __global__ void __launch_bounds__(kEwThreads) colsum_partial_kernel(const float*
     float s = 0.f;
     for (int gg = 0; gg < groups; ++gg) s += red[gg * cw + c];
     partial[(int64_t)blockIdx.x * C + col0 + c] = s;
+  }
+}
+
+// partial[b, 0:C] = sum_r w1[r,h(c)] x[r,c], partial[b, C:2C] = same with w2 (w == null -> 1); x bf16 [N, C], C = H*Ch
+__global__ void __launch_bounds__(kEwThreads) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w1,
+                                                                         const float* __restrict__ w2, int64_t N, int C, int H,
+                                                                         int rows_per_cta, float* __restrict__ partial) {
+  __shared__ float red[2][2048];  // groups * C <= 256 * 8
+  const int oct = C / 8;
+  const int groups = kEwThreads / oct;
+  const int g = threadIdx.x / oct, o = threadIdx.x % oct;
+  const int h = (o * 8) / (C / H);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(N, r0 + rows_per_cta);
+  float a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (g < groups) {
+    for (int64_t r = r0 + g; r < r1; r += groups) {
+      float f[8];
+      unpack8(ldg_stream(x + r * C + o * 8), f);
+      const float u1 = w1 ? w1[r * H + h] : 1.f;
+      const float u2 = w2 ? w2[r * H + h] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a1[i] = fmaf(u1, f[i], a1[i]); a2[i] = fmaf(u2, f[i], a2[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[0][g * C + o * 8 + i] = a1[i]; red[1][g * C + o * 8 + i] = a2[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += kEwThreads) {
+    const int which = c / C, cc = c % C;
+    float t = 0.f;
+    for (int gg = 0; gg < groups; ++gg) t += red[which][gg * C + cc];
+    partial[(int64_t)blockIdx.x * 2 * C + c] = t;
+  }
+}
+
+// dx = g0 + keep1 * g1 + keep2 * g2   (backward of mask_cast; any g may be null), bf16 grads -> fp32
+__global__ void __launch_bounds__(kEwThreads) mask_cast_bwd_kernel(const __nv_bfloat16* __restrict__ g0, const __nv_bfloat16* __restrict__ g1,
+                                                                   const __nv_bfloat16* __restrict__ g2, const uint8_t* __restrict__ keep1,
+                                                                   const uint8_t* __restrict__ keep2, int64_t n4, float* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g0) {
+      const uint2 u = reinterpret_cast<const uint2*>(g0)[i];
+      a[0] += __uint_as_float(u.x << 16); a[1] += __uint_as_float(u.x & 0xffff0000u);
+      a[2] += __uint_as_float(u.y << 16); a[3] += __uint_as_float(u.y & 0xffff0000u);
+    }
+    if (g1) {
+      const uint2 u = reinterpret_cast<const uint2*>(g1)[i];
+      const uint32_t m = reinterpret_cast<const uint32_t*>(keep1)[i];
+      if (m & 0xffu) a[0] += __uint_as_float(u.x << 16);
+      if (m & 0xff00u) a[1] += __uint_as_float(u.x & 0xffff0000u);
+      if (m & 0xff0000u) a[2] += __uint_as_float(u.y << 16);
+      if (m & 0xff000000u) a[3] += __uint_as_float(u.y & 0xffff0000u);
+    }
+    if (g2) {
+      const uint2 u = reinterpret_cast<const uint2*>(g2)[i];
+      const uint32_t m = reinterpret_cast<const uint32_t*>(keep2)[i];
+      if (m & 0xffu) a[0] += __uint_as_float(u.x << 16);
+      if (m & 0xff00u) a[1] += __uint_as_float(u.x & 0xffff0000u);
+      if (m & 0xff0000u) a[2] += __uint_as_float(u.y << 16);
+      if (m & 0xff000000u) a[3] += __uint_as_float(u.y & 0xffff0000u);
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(a[0], a[1], a[2], a[3]);
   }
 }
 
@@ -223,6 +296,41 @@ int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, i
   return BMKG_OK;
 }
 
+int bmkg_mask_cast_bwd(const void* g0, const void* g1, const void* g2, const uint8_t* keep1, const uint8_t* keep2, int64_t n,
+                       float* dx, void* stream) {
+  BMKG_REQUIRE(dx && n >= 0 && n % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE((!g1 || keep1) && (!g2 || keep2), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(dx), BMKG_ERR_MISALIGNED);
+  if (n == 0) return BMKG_OK;
+  mask_cast_bwd_kernel<<<ew_grid(n / 4), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(g0), static_cast<const __nv_bfloat16*>(g1), static_cast<const __nv_bfloat16*>(g2), keep1,
+      keep2, n / 4, dx);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_colsum_bf16(const void* x_bf16, const float* w1, const float* w2, int64_t N, int C, int H, float* out1, float* out2,
+                     void* ws, size_t ws_bytes, void* stream) {
+  // out1[c] = sum_r w1[r, head(c)] x[r, c] (w1 null -> plain column sum); out2 likewise with w2 (null -> skipped)
+  BMKG_REQUIRE(x_bf16 && out1 && N > 0 && H >= 1 && C % 8 == 0 && C >= 8 && C / 8 <= kEwThreads && C % H == 0 && (C / H) % 8 == 0,
+               BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(!w2 || out2, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(ws && ws_bytes >= 2 * bmkg_colsum_workspace_bytes(N, C), BMKG_ERR_WORKSPACE);
+  BMKG_REQUIRE(aligned16(x_bf16), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = colsum_ctas(N);
+  const int rows_per_cta = (int)ceil_div(N, nb);
+  float* partial = static_cast<float*>(ws);
+  colsum_bf16_partial_kernel<<<nb, kEwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), w1, w2, N, C, H, rows_per_cta,
+                                                        partial);
+  // partial rows are [out1 | out2] of width 2C: finish both halves with one launch over 2C columns, then split
+  // (out1/out2 need not be adjacent: two launches keep the ABI simple)
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial, nb, 2 * C, C, out1);
+  if (out2) colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial + C, nb, 2 * C, C, out2);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
 int bmkg_modality_mean(const float* x, int64_t N, int M, int F, float* out_f32, void* out_bf16, void* stream) {
   BMKG_REQUIRE(x && N > 0 && M > 0 && F > 0 && F % 4 == 0 && (out_f32 || out_bf16), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(aligned16(x), BMKG_ERR_MISALIGNED);
@@ -247,7 +355,7 @@ int bmkg_relu_dropout_bwd(const void* gy_bf16, const void* y_bf16, float scale, 
   relu_dropout_bwd_kernel<<<nb, kEwThreads, (size_t)groups * C * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(gy_bf16), static_cast<const __nv_bfloat16*>(y_bf16), scale, N, C, rows_per_cta,
       static_cast<__nv_bfloat16*>(gpre_bf16), static_cast<float*>(ws));
-  colsum_finish_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), nb, C, dbias);
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(static_cast<const float*>(ws), nb, C, C, dbias);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
@@ -261,7 +369,7 @@ int bmkg_colsum(const float* z, const float* row_weight, int64_t N, int C, float
   const int rows_per_cta = (int)ceil_div(N, nb);
   colsum_partial_kernel<<<dim3(nb, (unsigned)ceil_div(C, 1024)), kEwThreads, 0, st>>>(z, row_weight, N, C, rows_per_cta,
                                                                                        static_cast<float*>(ws));
-  colsum_finish_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(static_cast<const float*>(ws), nb, C, out);
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(static_cast<const float*>(ws), nb, C, C, out);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

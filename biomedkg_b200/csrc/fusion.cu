@@ -14,9 +14,16 @@ namespace bmkg {
 
 constexpr int kMaxOct = 4;  // octets (8 bf16) per lane per row: E <= 1024
 
+__device__ __forceinline__ void add_bias8(float* f, const float* __restrict__ b) {
+  if (!b) return;
+  const float4 b0 = *reinterpret_cast<const float4*>(b), b1 = *reinterpret_cast<const float4*>(b + 4);
+  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+}
+
+// qkv holds the bias-free projections x W^T; the [3E] bias (q|k|v) is added on load when given
 template <int M>
-__global__ void __launch_bounds__(256) fusion_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t N, int E,
-                                                              float* __restrict__ out, float* __restrict__ probs) {
+__global__ void __launch_bounds__(256) fusion_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
+                                                              int64_t N, int E, float* __restrict__ out, float* __restrict__ probs) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -35,6 +42,8 @@ __global__ void __launch_bounds__(256) fusion_attn_fwd_kernel(const __nv_bfloat1
       const __nv_bfloat16* rowp = qkv + ((n * M + m) * 3) * (int64_t)E;
       unpack8(ldg_stream(rowp + o * 8), q[m]);
       unpack8(ldg_stream(rowp + E + o * 8), k[m]);
+      add_bias8(q[m], bias ? bias + o * 8 : nullptr);
+      add_bias8(k[m], bias ? bias + E + o * 8 : nullptr);
     }
 #pragma unroll
     for (int i = 0; i < M; ++i)
@@ -82,6 +91,7 @@ __global__ void __launch_bounds__(256) fusion_attn_fwd_kernel(const __nv_bfloat1
     for (int j = 0; j < M; ++j) {
       float v[8];
       unpack8(ldg_stream(qkv + ((n * M + j) * 3 + 2) * (int64_t)E + o * 8), v);
+      add_bias8(v, bias ? bias + 2 * E + o * 8 : nullptr);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(wbar[j], v[e], acc[e]);
     }
@@ -94,9 +104,9 @@ __global__ void __launch_bounds__(256) fusion_attn_fwd_kernel(const __nv_bfloat1
 // dv_j = wbar_j dout ; dp_ij = (dout . v_j)/M ; ds_ij = p_ij (dp_ij - sum_j' p_ij' dp_ij')
 // dq_i = sum_j ds_ij k_j / sqrt(E) ; dk_j = sum_i ds_ij q_i / sqrt(E)
 template <int M>
-__global__ void __launch_bounds__(256) fusion_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ probs,
-                                                              const float* __restrict__ dout, int64_t N, int E,
-                                                              __nv_bfloat16* __restrict__ dqkv) {
+__global__ void __launch_bounds__(256) fusion_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias,
+                                                              const float* __restrict__ probs, const float* __restrict__ dout,
+                                                              int64_t N, int E, __nv_bfloat16* __restrict__ dqkv) {
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -120,6 +130,7 @@ __global__ void __launch_bounds__(256) fusion_attn_bwd_kernel(const __nv_bfloat1
     for (int j = 0; j < M; ++j) {
       float v[8], dv[8];
       unpack8(ldg_stream(qkv + ((n * M + j) * 3 + 2) * (int64_t)E + o * 8), v);
+      add_bias8(v, bias ? bias + 2 * E + o * 8 : nullptr);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         dv_dot[j] = fmaf(g[e], v[e], dv_dot[j]);
@@ -146,6 +157,8 @@ __global__ void __launch_bounds__(256) fusion_attn_bwd_kernel(const __nv_bfloat1
       const __nv_bfloat16* rowp = qkv + ((n * M + m) * 3) * (int64_t)E;
       unpack8(ldg_stream(rowp + o * 8), q[m]);
       unpack8(ldg_stream(rowp + E + o * 8), k[m]);
+      add_bias8(q[m], bias ? bias + o * 8 : nullptr);
+      add_bias8(k[m], bias ? bias + E + o * 8 : nullptr);
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) {
@@ -172,25 +185,26 @@ using namespace bmkg;
 
 extern "C" {
 
-int bmkg_fusion_attn_fwd(const void* qkv_bf16, int64_t N, int M, int E, float* out, float* probs, void* stream) {
+int bmkg_fusion_attn_fwd(const void* qkv_bf16, const float* qkv_bias, int64_t N, int M, int E, float* out, float* probs,
+                         void* stream) {
   BMKG_REQUIRE(qkv_bf16 && out && probs && N > 0, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(M >= 1 && M <= 4 && E % 8 == 0 && E > 0, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(aligned16(qkv_bf16) && aligned16(out), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(qkv_bf16) && aligned16(out) && (!qkv_bias || aligned16(qkv_bias)), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv_bf16);
   const unsigned grid = (unsigned)ceil_div(N, 8);
   switch (M) {
-    case 1: fusion_attn_fwd_kernel<1><<<grid, 256, 0, st>>>(q, N, E, out, probs); break;
-    case 2: fusion_attn_fwd_kernel<2><<<grid, 256, 0, st>>>(q, N, E, out, probs); break;
-    case 3: fusion_attn_fwd_kernel<3><<<grid, 256, 0, st>>>(q, N, E, out, probs); break;
-    default: fusion_attn_fwd_kernel<4><<<grid, 256, 0, st>>>(q, N, E, out, probs); break;
+    case 1: fusion_attn_fwd_kernel<1><<<grid, 256, 0, st>>>(q, qkv_bias, N, E, out, probs); break;
+    case 2: fusion_attn_fwd_kernel<2><<<grid, 256, 0, st>>>(q, qkv_bias, N, E, out, probs); break;
+    case 3: fusion_attn_fwd_kernel<3><<<grid, 256, 0, st>>>(q, qkv_bias, N, E, out, probs); break;
+    default: fusion_attn_fwd_kernel<4><<<grid, 256, 0, st>>>(q, qkv_bias, N, E, out, probs); break;
   }
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
 
-int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* probs, const float* dout, int64_t N, int M, int E, void* dqkv_bf16,
-                         void* stream) {
+int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* qkv_bias, const float* probs, const float* dout, int64_t N, int M,
+                         int E, void* dqkv_bf16, void* stream) {
   BMKG_REQUIRE(qkv_bf16 && probs && dout && dqkv_bf16 && N > 0, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(M >= 1 && M <= 4 && E % 8 == 0 && E > 0, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(aligned16(qkv_bf16) && aligned16(dout) && aligned16(dqkv_bf16), BMKG_ERR_MISALIGNED);
@@ -199,10 +213,10 @@ int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* probs, const float* 
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv_bf16);
   const unsigned grid = (unsigned)ceil_div(N, 8);
   switch (M) {
-    case 1: fusion_attn_bwd_kernel<1><<<grid, 256, 0, st>>>(q, probs, dout, N, E, dq); break;
-    case 2: fusion_attn_bwd_kernel<2><<<grid, 256, 0, st>>>(q, probs, dout, N, E, dq); break;
-    case 3: fusion_attn_bwd_kernel<3><<<grid, 256, 0, st>>>(q, probs, dout, N, E, dq); break;
-    default: fusion_attn_bwd_kernel<4><<<grid, 256, 0, st>>>(q, probs, dout, N, E, dq); break;
+    case 1: fusion_attn_bwd_kernel<1><<<grid, 256, 0, st>>>(q, qkv_bias, probs, dout, N, E, dq); break;
+    case 2: fusion_attn_bwd_kernel<2><<<grid, 256, 0, st>>>(q, qkv_bias, probs, dout, N, E, dq); break;
+    case 3: fusion_attn_bwd_kernel<3><<<grid, 256, 0, st>>>(q, qkv_bias, probs, dout, N, E, dq); break;
+    default: fusion_attn_bwd_kernel<4><<<grid, 256, 0, st>>>(q, qkv_bias, probs, dout, N, E, dq); break;
   }
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;

@@ -165,6 +165,25 @@ def colsum(z: torch.Tensor, row_weight: torch.Tensor | None = None) -> torch.Ten
     return out
 
 
+def colsum_bf16(x: torch.Tensor, w1=None, w2=None, heads: int = 1):
+    """Deterministic column sums of a bf16 [N,C] matrix, optionally weighted per (row, head) by w1 / w2 [N,H]."""
+    _need_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    N, C = x.shape
+    out1 = torch.empty(C, dtype=torch.float32, device=x.device)
+    out2 = torch.empty(C, dtype=torch.float32, device=x.device) if w2 is not None else None
+    ws = _ws(2 * lib.bmkg_colsum_workspace_bytes(N, C), x.device)
+    call("bmkg_colsum_bf16", _p(x), _p(w1), _p(w2), N, C, heads, _p(out1), _p(out2), _p(ws), ws.numel(), _stream())
+    return out1, out2
+
+
+def _colsum_any(g: torch.Tensor) -> torch.Tensor:
+    g = g.contiguous()
+    if g.dtype == BF16 and g.size(1) % 8 == 0 and g.size(1) <= 2048:
+        return colsum_bf16(g)[0]
+    return colsum(g.float())
+
+
 def _as_u8(m):
     if m is None:
         return None
@@ -189,13 +208,11 @@ class _MaskCastFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g0, g1, g2):
         keep1, keep2 = ctx.saved_tensors
-        g = None
-        for gi, k in ((g0, None), (g1, keep1), (g2, keep2)):
-            if gi is None:
-                continue
-            t = gi.float() if k is None else gi.float() * k.view(gi.shape)
-            g = t if g is None else g + t
-        return g, None, None, None
+        gs = [None if g is None else (g if g.dtype == BF16 else g.to(BF16)).contiguous() for g in (g0, g1, g2)]
+        ref = next(g for g in gs if g is not None)
+        dx = torch.empty(ref.shape, dtype=torch.float32, device=ref.device)
+        call("bmkg_mask_cast_bwd", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(keep1), _p(keep2), ref.numel(), _p(dx), _stream())
+        return dx, None, None, None
 
 
 def mask_cast(x, keep1=None, keep2=None, want_plain=True):
@@ -250,7 +267,7 @@ class _LinearFn(torch.autograd.Function):
         g16 = g.contiguous() if g.dtype == BF16 else g.to(BF16)
         dx = torch.mm(g16, w16).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
         dw = _mm_f32(g16.t(), x16) if ctx.needs_input_grad[1] else None
-        db = colsum(g.float()) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        db = _colsum_any(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
 
@@ -367,9 +384,8 @@ class _GATLayerFn(torch.autograd.Function):
         call("bmkg_gat_aggregate_bwd", _p(view.rowptr), _p(view.colind), _p(view.csc_rowptr), _p(view.csc_colind), _p(xh), _p(gpre),
              _p(a_s), _p(a_d), _p(rmax), _p(rsum), _p(atts), _p(attd), N, H, C, float(ctx.slope), _p(dxh), _p(das), _p(dad),
              _p(tsum), _stream())
-        xh3 = xh.view(N, H, C).float()
-        datt_s = torch.einsum("nh,nhc->hc", das, xh3).reshape(ctx.att_shape)
-        datt_d = torch.einsum("nh,nhc->hc", dad, xh3).reshape(ctx.att_shape)
+        datt_s, datt_d = colsum_bf16(xh, das, dad, H)          # d att_src[h,c] = sum_n d a_src[n,h] xh[n,h,c]
+        datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
         dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxh, w16) if ctx.needs_input_grad[0] else None
         return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None
@@ -466,29 +482,33 @@ def colmean_sigmoid(z):
 # fusion attention core
 # ---------------------------------------------------------------------------
 class _FusionAttnFn(torch.autograd.Function):
+    """qkv = bias-free x W^T (bf16 [N*M, 3E]); the q|k|v bias [3E] is added inside the kernel."""
+
     @staticmethod
-    def forward(ctx, qkv, N, M, E):
+    def forward(ctx, qkv, bias, N, M, E):
         _need_cuda(qkv)
         assert qkv.dtype == BF16 and qkv.is_contiguous()
+        b = None if bias is None else bias.detach().float().contiguous()
         out = torch.empty(N, E, dtype=torch.float32, device=qkv.device)
         probs = torch.empty(N, M, M, dtype=torch.float32, device=qkv.device)
-        call("bmkg_fusion_attn_fwd", _p(qkv), N, M, E, _p(out), _p(probs), _stream())
-        ctx.save_for_backward(qkv, probs)
+        call("bmkg_fusion_attn_fwd", _p(qkv), _p(b), N, M, E, _p(out), _p(probs), _stream())
+        ctx.save_for_backward(qkv, probs, b)
         ctx.dims = (N, M, E)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        qkv, probs = ctx.saved_tensors
+        qkv, probs, b = ctx.saved_tensors
         N, M, E = ctx.dims
         g = g.contiguous().float()
         dqkv = torch.empty_like(qkv)
-        call("bmkg_fusion_attn_bwd", _p(qkv), _p(probs), _p(g), N, M, E, _p(dqkv), _stream())
-        return dqkv, None, None, None
+        call("bmkg_fusion_attn_bwd", _p(qkv), _p(b), _p(probs), _p(g), N, M, E, _p(dqkv), _stream())
+        db = colsum_bf16(dqkv)[0] if (b is not None and ctx.needs_input_grad[1]) else None
+        return dqkv, db, None, None, None
 
 
-def fusion_attention(qkv, N, M, E):
-    return _FusionAttnFn.apply(qkv, N, M, E)
+def fusion_attention(qkv, bias, N, M, E):
+    return _FusionAttnFn.apply(qkv, bias, N, M, E)
 
 
 # ---------------------------------------------------------------------------

@@ -24,8 +24,8 @@ class AttentionFusion(nn.Module):
         N, M, E = x.shape
         w = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], dim=0)
         b = torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_proj.bias], dim=0)
-        qkv = ops.linear(x.reshape(N * M, E), w, b, out_bf16=True)
-        return ops.fusion_attention(qkv.contiguous(), N, M, E)
+        qkv = ops.linear(x.reshape(N * M, E), w, None, out_bf16=True)     # bias is added inside the fused kernel
+        return ops.fusion_attention(qkv.contiguous(), b, N, M, E)
 
 
 class ReDAF(nn.Module):

@@ -96,6 +96,13 @@ int bmkg_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* colind, const i
  * bmkg_l2norm_scale(_bwd): F.normalize of PyGCL's _similarity fused with the sqrt(log2e/tau) scale. */
 int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, int64_t n, void* x0_bf16, void* x1_bf16,
                    void* x2_bf16, void* stream);
+/* backward of bmkg_mask_cast: dx = g0 + keep1*g1 + keep2*g2 (bf16 grads, any NULL) -> fp32 */
+int bmkg_mask_cast_bwd(const void* g0_bf16, const void* g1_bf16, const void* g2_bf16, const uint8_t* keep1, const uint8_t* keep2,
+                       int64_t n, float* dx, void* stream);
+/* deterministic column sums of a bf16 [N, C = H*Ch] matrix, optionally weighted per (row, head): out1 with w1 [N,H]
+ * (NULL = 1), out2 with w2 (NULL = skipped).  GAT attention-vector gradients and bf16 bias gradients. ws >= 2x colsum ws. */
+int bmkg_colsum_bf16(const void* x_bf16, const float* w1, const float* w2, int64_t num_rows, int channels, int heads, float* out1,
+                     float* out2, void* ws, size_t ws_bytes, void* stream);
 int bmkg_modality_mean(const float* x, int64_t num_nodes, int modalities, int features, float* out_f32, void* out_bf16,
                        void* stream);
 size_t bmkg_colsum_workspace_bytes(int64_t num_rows, int channels);
@@ -122,12 +129,13 @@ int bmkg_softplus_pair_bwd(const float* s_pos, const float* s_neg, const float* 
 
 /* ---- F1: modality-fusion attention core ---------------------------------------------------
  * F.scaled_dot_product_attention over the modality axis + mean (biomedkg/utils/fusion.py:22-29).
- * qkv bf16 [N*M, 3E] (row = [q|k|v] of one (node, modality)); out fp32 [N,E]; probs fp32 [N,M,M]
+ * qkv bf16 [N*M, 3E] (row = [q|k|v] of one (node, modality), bias-free x W^T); qkv_bias fp32 [3E] or NULL is
+ * added on load; out fp32 [N,E]; probs fp32 [N,M,M]
  * saved for the backward; M <= 4, E % 8 == 0. */
-int bmkg_fusion_attn_fwd(const void* qkv_bf16, int64_t num_nodes, int modalities, int embed, float* out, float* probs,
-                         void* stream);
-int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* probs, const float* dout, int64_t num_nodes, int modalities,
-                         int embed, void* dqkv_bf16, void* stream);
+int bmkg_fusion_attn_fwd(const void* qkv_bf16, const float* qkv_bias, int64_t num_nodes, int modalities, int embed, float* out,
+                         float* probs, void* stream);
+int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* qkv_bias, const float* probs, const float* dout, int64_t num_nodes,
+                         int modalities, int embed, void* dqkv_bf16, void* stream);
 
 /* ---- I1/I2: fused GRACE InfoNCE (tcgen05 / TMEM / TMA) -----------------------------------
  * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).

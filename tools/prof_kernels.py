@@ -1,0 +1,50 @@
+"""Small driver for ncu captures: runs the hot kernels stand-alone at a BASELINE config size.
+    ncu --set full --clock-control none --import-source on -k regex:infonce -s 2 -c 2 -o gpurun_out/prof python tools/prof_kernels.py infonce 28000
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from biomedkg_b200 import ops
+
+what, n = sys.argv[1], int(sys.argv[2])
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = "cuda"
+torch.manual_seed(0)
+if what == "infonce":
+    h1 = torch.randn(n, 256, device=dev, requires_grad=True)
+    h2 = (h1.detach() + torch.randn(n, 256, device=dev)).requires_grad_(True)
+    for _ in range(iters):
+        loss = ops.infonce_loss(h1, h2, 0.2)
+        loss.backward()
+    torch.cuda.synchronize()
+    e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e0.record()
+    loss = ops.infonce_loss(h1, h2, 0.2)
+    e1.record()
+    loss.backward()
+    e2.record()
+    torch.cuda.synchronize()
+    f, b = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    print(f"N={n} fwd {f:.3f} ms ({6*n*n*256/f/1e9:.0f} TF/s credited)  bwd {b:.3f} ms ({8*n*n*256/b/1e9:.0f} TF/s credited) loss {float(loss):.5f}")
+elif what in ("gcn", "gat"):
+    e = int(sys.argv[4]) if len(sys.argv) > 4 else n * 23
+    ei = torch.randint(0, n, (2, e), device=dev)
+    view = ops.SortedGraph(ei, n).view(torch.rand(e, device=dev) >= 0.4)
+    x = torch.randn(n, 256, device=dev).bfloat16()
+    bias = torch.zeros(256, device=dev)
+    nnz = int(view.nnz.item())
+    for _ in range(iters):
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    byts = nnz * (256 * 2 + 4) + n * 256 * 2 + 4 * (n + 1)
+    print(f"gcn_aggregate N={n} nnz={nnz}: {ms*1e3:.1f} us, {byts/ms/1e6:.0f} GB/s algorithmic")
