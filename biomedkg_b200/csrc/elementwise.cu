@@ -150,9 +150,10 @@ __global__ void __launch_bounds__(kEwThreads) colsum_partial_kernel(const float*
 }
 
 // partial[b, 0:C] = sum_r w1[r,h(c)] x[r,c], partial[b, C:2C] = same with w2 (w == null -> 1); x bf16 [N, C], C = H*Ch
-__global__ void __launch_bounds__(kEwThreads) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w1,
-                                                                         const float* __restrict__ w2, int64_t N, int C, int H,
-                                                                         int rows_per_cta, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kEwThreads) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld,
+                                                                         const float* __restrict__ w1, const float* __restrict__ w2,
+                                                                         int64_t N, int C, int H, int rows_per_cta,
+                                                                         float* __restrict__ partial) {
   __shared__ float red[2][2048];  // groups * C <= 256 * 8
   const int oct = C / 8;
   const int groups = kEwThreads / oct;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kEwThreads) colsum_bf16_partial_kernel(const _
   if (g < groups) {
     for (int64_t r = r0 + g; r < r1; r += groups) {
       float f[8];
-      unpack8(ldg_stream(x + r * C + o * 8), f);
+      unpack8(ldg_stream(x + r * ld + o * 8), f);
       const float u1 = w1 ? w1[r * H + h] : 1.f;
       const float u2 = w2 ? w2[r * H + h] : 0.f;
 #pragma unroll
@@ -312,8 +313,8 @@ int bmkg_mask_cast_bwd(const void* g0, const void* g1, const void* g2, const uin
 int bmkg_colsum_bf16(const void* x_bf16, const float* w1, const float* w2, int64_t N, int C, int H, float* out1, float* out2,
                      void* ws, size_t ws_bytes, void* stream) {
   // out1[c] = sum_r w1[r, head(c)] x[r, c] (w1 null -> plain column sum); out2 likewise with w2 (null -> skipped)
-  BMKG_REQUIRE(x_bf16 && out1 && N > 0 && H >= 1 && C % 8 == 0 && C >= 8 && C / 8 <= kEwThreads && C % H == 0 && (C / H) % 8 == 0,
-               BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(x_bf16 && out1 && N > 0 && H >= 1 && C % 8 == 0 && C >= 8 && C % H == 0 && (C / H) % 8 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(C <= 2048 || (H == 1 && !w2), BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(!w2 || out2, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(ws && ws_bytes >= 2 * bmkg_colsum_workspace_bytes(N, C), BMKG_ERR_WORKSPACE);
   BMKG_REQUIRE(aligned16(x_bf16), BMKG_ERR_MISALIGNED);
@@ -321,12 +322,13 @@ int bmkg_colsum_bf16(const void* x_bf16, const float* w1, const float* w2, int64
   const int nb = colsum_ctas(N);
   const int rows_per_cta = (int)ceil_div(N, nb);
   float* partial = static_cast<float*>(ws);
-  colsum_bf16_partial_kernel<<<nb, kEwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), w1, w2, N, C, H, rows_per_cta,
-                                                        partial);
-  // partial rows are [out1 | out2] of width 2C: finish both halves with one launch over 2C columns, then split
-  // (out1/out2 need not be adjacent: two launches keep the ABI simple)
-  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial, nb, 2 * C, C, out1);
-  if (out2) colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial + C, nb, 2 * C, C, out2);
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+  for (int c0 = 0; c0 < C; c0 += 2048) {  // 2048-column slabs (one launch when C <= 2048)
+    const int cw = (C - c0) < 2048 ? (C - c0) : 2048;
+    colsum_bf16_partial_kernel<<<nb, kEwThreads, 0, st>>>(x + c0, C, w1, w2, N, cw, H, rows_per_cta, partial);
+    colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), 256, 0, st>>>(partial, nb, 2 * cw, cw, out1 + c0);
+    if (out2) colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), 256, 0, st>>>(partial + cw, nb, 2 * cw, cw, out2 + c0);
+  }
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

@@ -24,6 +24,7 @@
 //
 // Tensor-bound.  Algorithmic FLOPs: fwd 6 N^2 D, bwd 8 N^2 D.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -33,15 +34,18 @@ namespace bmkg {
 namespace nce {
 
 constexpr int kBM = 128;             // rows of Z per CTA work item (UMMA M)
-constexpr int kBN = 128;             // rows of Z per streamed column tile (UMMA N)
+constexpr int kBN = 128;             // forward: rows of Z per streamed column tile (UMMA N)
+constexpr int kBNb = 64;             // backward: column-tile rows (UMMA N of MMA1, K of MMA2)
 constexpr int kPanelElems = 64;      // 64 bf16 = 128 B = one swizzle row
-constexpr int kPanelBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kMaxPanels = 4;        // D <= 256
-constexpr int kStages = 2;
-constexpr int kAccBufs = 4;          // fwd: 4 x 128 TMEM columns
 constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2-9 softmax (2 warpgroups)
 constexpr int kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kPanelBytes * kMaxPanels * (1 + kStages) + 256 /*barriers*/;
+// forward: 3 stages of (128 rows x 512 B); backward: 5 stages of (64 rows x 512 B).  The stationary row block (A) lives in
+// TMEM, not smem: the SS form would re-read it from shared memory for every MMA and the kernels are smem-bandwidth bound.
+constexpr int kFwdStages = 3, kFwdAcc = 3, kFwdPanelBytes = kBN * 128;
+constexpr int kBwdStages = 5, kBwdPanelBytes = kBNb * 128;
+constexpr size_t kFwdSmemBytes = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages + 256;
+constexpr size_t kBwdSmemBytes = 1024 + (size_t)kBwdPanelBytes * kMaxPanels * kBwdStages + 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -53,34 +57,55 @@ struct Schedule {
   int nrb, ntiles, nchunks, tiles_per_chunk;
 };
 
+// Stationary operand: the calling warp writes 32 rows of Z (one per lane, bf16 pairs packed per 32-bit TMEM column,
+// the layout tcgen05.mma expects for an A operand in tensor memory) into TMEM columns [col0, col0 + D/2).
+__device__ __forceinline__ void stage_rows_to_tmem(const __nv_bfloat16* __restrict__ z, int rows, int D, int row,
+                                                   uint32_t lane_addr) {
+  const uint4* src = reinterpret_cast<const uint4*>(z + (size_t)row * D);
+  for (int i = 0; i < D / 32; ++i) {  // 32 bf16 = 4 x uint4 = 16 TMEM columns per step
+    uint32_t v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (row < rows) u = __ldg(src + i * 4 + q);
+      v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+    }
+    ptx::tmem_st16(lane_addr + (uint32_t)i * 16u, v);
+  }
+  ptx::tmem_st_wait();
+}
+
 // ----------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------
+// TMEM map: [0,128) stationary rows A (bf16), [128 + 128 i, +128) accumulator ring i = 0..2.
+template <int NP>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int npanels, Schedule sch, int rows_padded,
-                   float* __restrict__ partial) {
+infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
+                   const __nv_bfloat16* __restrict__ z, float* __restrict__ partial) {
+  constexpr int D = NP * kPanelElems;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kPanelBytes * kMaxPanels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPanelBytes * kMaxPanels * (1 + kStages));
-  uint64_t* full = bars;                  // [kStages]
-  uint64_t* empty = bars + kStages;       // [kStages]
-  uint64_t* a_full = bars + 2 * kStages;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* tfull = a_empty + 1;          // [kAccBufs]
-  uint64_t* tempty = tfull + kAccBufs;    // [kAccBufs]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccBufs);
+  uint8_t* sB = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages);
+  uint64_t* full = bars;                       // [kFwdStages]
+  uint64_t* empty = full + kFwdStages;         // [kFwdStages]
+  uint64_t* a_full = empty + kFwdStages;       // stationary rows staged in TMEM (4 warp arrivals)
+  uint64_t* a_empty = a_full + 1;              // every MMA of the work item retired
+  uint64_t* tfull = a_empty + 1;               // [kFwdAcc]
+  uint64_t* tempty = tfull + kFwdAcc;          // [kFwdAcc]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kFwdAcc);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(a_full, 1);
+    for (int s = 0; s < kFwdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(a_full, 4);
     ptx::mbar_init(a_empty, 1);
-    for (int b = 0; b < kAccBufs; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
+    for (int b = 0; b < kFwdAcc; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmap);
   }
@@ -91,86 +116,92 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int npane
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_items = sch.nrb * sch.nchunks;
-  const uint32_t tile_bytes = (uint32_t)npanels * kPanelBytes;
+  const uint32_t tile_bytes = (uint32_t)npanels * kFwdPanelBytes;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
+    if (lane == 0) {  // ---------------- TMA producer: column tiles only ----------------
       int stage = 0;
-      uint32_t sphase = 0, aphase = 0;
+      uint32_t sphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int rb = item / sch.nchunks, cc = item % sch.nchunks;
-        ptx::mbar_wait(a_empty, aphase ^ 1);
-        ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
-        for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPanelBytes, &tmap, a_full, p * kPanelElems, rb * kBM);
-        aphase ^= 1;
+        const int cc = item % sch.nchunks;
         const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
         for (int ct = t0; ct < t1; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
-          uint8_t* dst = sB + (size_t)stage * kPanelBytes * kMaxPanels;
-          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
-          if (++stage == kStages) { stage = 0; sphase ^= 1; }
+          uint8_t* dst = sB + (size_t)stage * kFwdPanelBytes * kMaxPanels;
+          for (int p = 0; p < npanels; ++p)
+            ptx::tma_load_2d(dst + p * kFwdPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          if (++stage == kFwdStages) { stage = 0; sphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
+    {  // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues): S = A(tmem) * B(smem)^T ----------------
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);
       int stage = 0, acc = 0;
       uint32_t sphase = 0, accphase = 0, aphase = 0;
-      const uint32_t a_addr = ptx::smem_u32(sA);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cc = item % sch.nchunks;
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
+        ptx::tc_fence_after();
         const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
         for (int ct = t0; ct < t1; ++ct) {
           ptx::mbar_wait(&tempty[acc], accphase ^ 1);
           ptx::mbar_wait(&full[stage], sphase);
           ptx::tc_fence_after();
-          const uint32_t b_addr = ptx::smem_u32(sB + (size_t)stage * kPanelBytes * kMaxPanels);
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kBN;
-          const int ksteps = npanels * 4;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t off = (uint32_t)(kk >> 2) * kPanelBytes + (uint32_t)(kk & 3) * 32u;
-            ptx::umma_ss(d_tmem, ptx::smem_desc_sw128(a_addr + off, 16, 1024), ptx::smem_desc_sw128(b_addr + off, 16, 1024),
-                         idesc, kk > 0 ? 1u : 0u);
+          // one descriptor per stage, advanced per K step by a compile-time constant (start-address field, 16 B units):
+          // keeps the single issuing thread at a few instructions per tcgen05.mma
+          const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + (size_t)stage * kFwdPanelBytes * kMaxPanels), 16, 1024);
+          const uint32_t d_tmem = tmem_base + 128u + (uint32_t)acc * kBN;
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < NP * 4; ++kk) {
+              const uint32_t off16 = (uint32_t)(((kk >> 2) * kFwdPanelBytes + (kk & 3) * 32) >> 4);
+              ptx::umma_ts(d_tmem, tmem_base + (uint32_t)kk * 8u, bdesc + off16, idesc, kk > 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty[stage]);
+            ptx::umma_commit(&tfull[acc]);
           }
-          ptx::umma_commit(&empty[stage]);
-          ptx::umma_commit(&tfull[acc]);
-          if (++stage == kStages) { stage = 0; sphase ^= 1; }
-          if (++acc == kAccBufs) { acc = 0; accphase ^= 1; }
+          __syncwarp();
+          if (++stage == kFwdStages) { stage = 0; sphase ^= 1; }
+          if (++acc == kFwdAcc) { acc = 0; accphase ^= 1; }
         }
-        ptx::umma_commit(a_empty);
+        if (ptx::elect_one()) ptx::umma_commit(a_empty);
+        __syncwarp();
       }
     }
   } else {  // ---------------- softmax warpgroups ----------------
     const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int lrow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int tcount = 0;
+    uint32_t aphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rb = item / sch.nchunks, cc = item % sch.nchunks;
       const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
+      if (wg == 0) {  // stage this item's 128 stationary rows into TMEM once the previous item's MMAs retired
+        ptx::mbar_wait(a_empty, aphase ^ 1);
+        aphase ^= 1;
+        ptx::tc_fence_after();
+        stage_rows_to_tmem(z, rows, D, rb * kBM + lrow, lane_base);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full);
+      }
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       for (int ct = t0; ct < t1; ++ct, ++tcount) {
         if ((tcount & 1) != wg) continue;
-        const int acc = tcount & (kAccBufs - 1);
-        const uint32_t ph = (uint32_t)(tcount / kAccBufs) & 1u;
+        const int acc = tcount % kFwdAcc;
+        const uint32_t ph = (uint32_t)(tcount / kFwdAcc) & 1u;
         ptx::mbar_wait(&tfull[acc], ph);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kBN;
+        const uint32_t taddr = lane_base + 128u + (uint32_t)acc * kBN;
         const bool diag = (ct == rb);
-#pragma unroll
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (c == kBN / 32 - 1) {  // accumulator fully in registers: hand the buffer back
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-          }
+        // 128 columns in 4 chunks of 32, loads issued two chunks ahead of the exp/sum so TMEM latency is hidden
+        uint32_t ra[32], rb_[32];
+        auto consume = [&](uint32_t (&r)[32], int c) {
           if (diag) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -183,7 +214,21 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int npane
             s2 += ex2(__uint_as_float(r[j + 2]));
             s3 += ex2(__uint_as_float(r[j + 3]));
           }
-        }
+        };
+        ptx::tmem_ld32(taddr, ra);
+        ptx::tmem_ld32(taddr + 32, rb_);
+        ptx::tmem_ld_wait();
+        consume(ra, 0);
+        ptx::tmem_ld32(taddr + 64, ra);
+        consume(rb_, 1);
+        ptx::tmem_ld32(taddr + 96, rb_);
+        ptx::tmem_ld_wait();
+        // accumulator fully in registers: hand the buffer back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        consume(ra, 2);
+        consume(rb_, 3);
       }
       const int row = rb * kBM + lrow;
       if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s0 + s1) + (s2 + s3);
@@ -245,37 +290,46 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // backward
 // ----------------------------------------------------------------------------
 // TMEM map: [0,256) dZ accumulator (128 x D fp32), [256,384) S/P buffer 0, [384,512) S/P buffer 1.
+// Column tiles are 128 rows of Z.  MMA1: S[128x128] = Z_U Z_V^T (both operands in smem, K-major).  The two softmax
+// warpgroups turn 64 columns each into bf16 P in place (aliasing their own S columns).  MMA2: dZ[128xD] += P(tmem) * Z_V with
+// the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
+// may be issued into the buffer MMA2(t) still reads without waiting for MMA2(t) to complete.
+constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
+constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256;
+
+template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int D, int npanels, int nrb, int ntiles,
-                   const float* __restrict__ inv_r /*[ntiles*128], zero padded*/, const float* __restrict__ gscale,
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int nrb, int ntiles,
+                   const float* __restrict__ inv_r /*[>= ntiles*128], zero padded*/, const float* __restrict__ gscale,
                    const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
+  constexpr int D = NP * kPanelElems;
+  constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kPanelBytes * kMaxPanels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPanelBytes * kMaxPanels * (1 + kStages));
-  uint64_t* full = bars;             // [2] V tile landed
-  uint64_t* empty = bars + 2;        // [2] V tile no longer needed (MMA2 done)
-  uint64_t* a_full = bars + 4;
-  uint64_t* a_empty = bars + 5;
-  uint64_t* s_full = bars + 6;       // [2] S = Z_U Z_V^T ready in TMEM
-  uint64_t* p_full = bars + 8;       // [2] P written back to TMEM (4 warp arrivals)
-  uint64_t* sp_empty = bars + 10;    // [2] MMA2 finished reading P
-  uint64_t* dz_full = bars + 12;
-  uint64_t* dz_empty = bars + 13;    // 8 warp arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint8_t* sB = smem + kPB * kMaxPanels;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
+  uint64_t* full = bars;                    // [2] V tile landed
+  uint64_t* empty = full + 2;               // [2] V tile no longer needed (MMA2 done)
+  uint64_t* a_full = empty + 2;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* s_full = a_empty + 1;           // [2] S ready in TMEM
+  uint64_t* p_full = s_full + 2;            // [2][4] P written back per 32-column quarter (4 warp arrivals each)
+  uint64_t* dz_full = p_full + 8;
+  uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_full[s], 4);
-      ptx::mbar_init(&sp_empty[s], 1);
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
     }
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
@@ -289,7 +343,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tile_bytes = (uint32_t)npanels * kPanelBytes;
+  const uint32_t tile_bytes = (uint32_t)npanels * kPB;
+  constexpr uint32_t kColS = 256u;
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer ----------------
@@ -298,62 +353,92 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
       for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_empty, aphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
-        for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPanelBytes, &tmap, a_full, p * kPanelElems, rb * kBM);
+        for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
         aphase ^= 1;
         for (int ct = 0; ct < ntiles; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
-          uint8_t* dst = sB + (size_t)stage * kPanelBytes * kMaxPanels;
-          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
-          if (++stage == kStages) { stage = 0; sphase ^= 1; }
+          uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
+          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          if (++stage == kBwdStagesA) { stage = 0; sphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T     (A,B K-major)
-      const uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);        // dZ += P Z_V       (A tmem, B MN-major)
-      const uint32_t a_addr = ptx::smem_u32(sA);
-      uint32_t tcount = 0;  // global tile counter of this CTA: stage = buf = tcount & 1, phase = (tcount >> 1) & 1
+    {  // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
+      constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T   (A, B K-major in smem)
+      constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);    // dZ += P Z_V     (A tmem, B MN-major)
+      const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA), 16, 1024);
+      uint64_t bdesc_k[2], bdesc_mn[2];  // per stage: K-major view (MMA1) and MN-major view (MMA2) of the same tile
+      for (int st = 0; st < 2; ++st) {
+        const uint32_t a = ptx::smem_u32(sB + (size_t)st * kPB * kMaxPanels);
+        bdesc_k[st] = ptx::smem_desc_sw128(a, 16, 1024);
+        bdesc_mn[st] = ptx::smem_desc_sw128(a, kPB, 1024);
+      }
+      uint32_t tcount = 0;  // global tile counter of this CTA: stage = buffer = tcount & 1, phase = (tcount >> 1) & 1
       uint32_t aphase = 0, dzphase = 0;
       auto issue_mma1 = [&](uint32_t tc) {
         const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
-        ptx::mbar_wait(&sp_empty[b], ph ^ 1u);
         ptx::mbar_wait(&full[b], ph);
         ptx::tc_fence_after();
-        const uint32_t b_addr = ptx::smem_u32(sB + (size_t)b * kPanelBytes * kMaxPanels);
-        const uint32_t d_tmem = tmem_base + 256u + b * 128u;
-        const int ksteps = npanels * 4;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 2) * kPanelBytes + (uint32_t)(kk & 3) * 32u;
-          ptx::umma_ss(d_tmem, ptx::smem_desc_sw128(a_addr + off, 16, 1024), ptx::smem_desc_sw128(b_addr + off, 16, 1024), idesc1,
-                       kk > 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + kColS + b * 128u;
+        const uint64_t bd = bdesc_k[b];
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < NP * 4; ++kk) {
+            const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
+            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&s_full[b]);
         }
-        ptx::umma_commit(&s_full[b]);
+        __syncwarp();
       };
       for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::mbar_wait(dz_empty, dzphase ^ 1);
-        issue_mma1(tcount);
-        for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
-          if (ct + 1 < ntiles) issue_mma1(tcount + 1);
-          const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
-          ptx::mbar_wait(&p_full[b], ph);
-          ptx::tc_fence_after();
-          const uint32_t b_addr = ptx::smem_u32(sB + (size_t)b * kPanelBytes * kMaxPanels);
-          const uint32_t p_tmem = tmem_base + 256u + b * 128u;
-          // K = 128 rows of the V tile, 16 per step: MN-major B, 8-row groups 1024 B apart (SBO),
-          // 64-feature panels kPanelBytes apart (LBO)
-          for (int k = 0; k < kBN / 16; ++k) {
-            ptx::umma_ts(tmem_base, p_tmem + (uint32_t)k * 8u, ptx::smem_desc_sw128(b_addr + (uint32_t)k * 2048u, kPanelBytes, 1024),
-                         idesc2, (ct > 0 || k > 0) ? 1u : 0u);
+        // Issue order MMA1(t) MMA1(t+1) | MMA2(t) MMA2(t+1) MMA1(t+2) MMA1(t+3) | ...: with two smem stages and two S/P
+        // buffers this puts one full MMA (1024 tensor cycles) between "stage freed by MMA2(t)" and "MMA1(t+2) needs the
+        // reloaded stage", and between "S(t) ready" and "MMA2(t) needs P(t)", instead of exposing those latencies.
+        auto issue_mma2 = [&](uint32_t tc, bool first) {
+          const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
+          const uint64_t bmn = bdesc_mn[b];
+          const uint32_t p_tmem = tmem_base + kColS + b * 128u;
+          // K = 128 rows of the V tile, 16 per step.  MN-major B: 8-row groups 1024 B apart (SBO), 64-feature panels kPB
+          // apart (LBO).  P of columns [64w, 64w+64) sits (bf16 pairs) in TMEM columns [64w, 64w+32) of the S buffer.
+          // The softmax warpgroups publish P per 32-column quarter (q = 2*chunk + wg), so the first K steps start while
+          // the second chunk is still being exponentiated: quarter q covers columns [64 wg + 32 chunk, +32) = K steps
+          // 4 wg + 2 chunk, +1.
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ptx::mbar_wait(&p_full[b * 4 + q], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const int k0 = 4 * (q & 1) + 2 * (q >> 1);
+#pragma unroll
+              for (int k = k0; k < k0 + 2; ++k) {
+                ptx::umma_ts(tmem_base, p_tmem + (uint32_t)(k >> 2) * 64u + (uint32_t)(k & 3) * 8u, bmn + (uint32_t)(k * 2048 >> 4),
+                             idesc2, (!first || q > 0 || k > k0) ? 1u : 0u);
+              }
+              if (q == 3) ptx::umma_commit(&empty[b]);
+            }
+            __syncwarp();
           }
-          ptx::umma_commit(&empty[b]);
-          ptx::umma_commit(&sp_empty[b]);
+        };
+        issue_mma1(tcount);
+        if (ntiles > 1) issue_mma1(tcount + 1);
+        for (int ct = 0; ct < ntiles; ct += 2) {
+          issue_mma2(tcount + ct, ct == 0);
+          if (ct + 1 < ntiles) issue_mma2(tcount + ct + 1, false);
+          if (ct + 2 < ntiles) issue_mma1(tcount + ct + 2);
+          if (ct + 3 < ntiles) issue_mma1(tcount + ct + 3);
         }
-        ptx::umma_commit(dz_full);
-        ptx::umma_commit(a_empty);
+        tcount += (uint32_t)ntiles;
+        if (ptx::elect_one()) {
+          ptx::umma_commit(dz_full);
+          ptx::umma_commit(a_empty);
+        }
+        __syncwarp();
         dzphase ^= 1;
       }
     }
@@ -367,49 +452,292 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
     for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
       const float cu = inv_r[row];  // padded with zeros beyond `rows`
+      const int colbase = wg * 64;
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
-        if ((int)(tcount & 1u) != wg) continue;
+        // every tile is split between the two warpgroups (64 columns each)
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+        const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
+        const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
+        const float4* cvp = reinterpret_cast<const float4*>(inv_r + gcol0);
+        float4 cvr[16];  // 1/R of this tile's columns: fetched before the wait so the load latency is off the S -> P chain
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
         ptx::mbar_wait(&s_full[b], ph);
         ptx::tc_fence_after();
-        const uint32_t taddr = lane_base + 256u + b * 128u;
-        const bool diag = (ct == rb);
-        const float4* cvp = reinterpret_cast<const float4*>(inv_r + (size_t)ct * kBN);
-#pragma unroll
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-          uint32_t pk[16];
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(taddr, r0);
+        ptx::tmem_ld32(taddr + 32, r1);
+        ptx::tmem_ld_wait();
+        const bool diag = (row >= gcol0) && (row < gcol0 + 64);
+        auto make_p = [&](const uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 cv = __ldg(cvp + c * 8 + q);
+            const float4 cv = cvr[c * 8 + q];
             float p0 = ex2(__uint_as_float(r[4 * q + 0])) * (cu + cv.x);
             float p1 = ex2(__uint_as_float(r[4 * q + 1])) * (cu + cv.y);
             float p2 = ex2(__uint_as_float(r[4 * q + 2])) * (cu + cv.z);
             float p3 = ex2(__uint_as_float(r[4 * q + 3])) * (cu + cv.w);
             if (diag) {
-              const int j = c * 32 + 4 * q;
-              if (j + 0 == lrow) p0 = 0.f;
-              if (j + 1 == lrow) p1 = 0.f;
-              if (j + 2 == lrow) p2 = 0.f;
-              if (j + 3 == lrow) p3 = 0.f;
+              const int j = gcol0 + c * 32 + 4 * q;
+              if (j + 0 == row) p0 = 0.f;
+              if (j + 1 == row) p1 = 0.f;
+              if (j + 2 == row) p2 = 0.f;
+              if (j + 3 == row) p3 = 0.f;
             }
             pk[2 * q] = pack2(p0, p1);
             pk[2 * q + 1] = pack2(p2, p3);
           }
-          ptx::tmem_st16(taddr + c * 16, pk);  // P (bf16 pairs) aliases the S columns already consumed
-        }
+        };
+        uint32_t pk[16];
+        make_p(r0, 0, pk);
+        ptx::tmem_st16(taddr, pk);  // P (bf16 pairs) aliases this warpgroup's own, already consumed, S columns
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + wg]);        // quarter 0/1: first 32 columns of this warpgroup
+        make_p(r1, 1, pk);
+        ptx::tmem_st16(taddr + 16, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + 2 + wg]);    // quarter 2/3: second 32 columns
       }
       // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D)
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
       const int half = D / 2;
+      const int pair = (row < N) ? row + N : row - N;
+      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (row < rows) {
+          const uint4* zp = reinterpret_cast<const uint4*>(z + (size_t)pair * D + c0);
+          float* out = dz + (size_t)row * D + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(__ldg(zp + q), f);
+            float4 o0, o1;
+            o0.x = gcoef * (__uint_as_float(r[8 * q + 0]) - 2.f * f[0]);
+            o0.y = gcoef * (__uint_as_float(r[8 * q + 1]) - 2.f * f[1]);
+            o0.z = gcoef * (__uint_as_float(r[8 * q + 2]) - 2.f * f[2]);
+            o0.w = gcoef * (__uint_as_float(r[8 * q + 3]) - 2.f * f[3]);
+            o1.x = gcoef * (__uint_as_float(r[8 * q + 4]) - 2.f * f[4]);
+            o1.y = gcoef * (__uint_as_float(r[8 * q + 5]) - 2.f * f[5]);
+            o1.z = gcoef * (__uint_as_float(r[8 * q + 6]) - 2.f * f[6]);
+            o1.w = gcoef * (__uint_as_float(r[8 * q + 7]) - 2.f * f[7]);
+            *reinterpret_cast<float4*>(out + 8 * q) = o0;
+            *reinterpret_cast<float4*>(out + 8 * q + 4) = o1;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dz_empty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------
+// backward, variant B: 64-row column tiles with the stationary block in TMEM
+// ----------------------------------------------------------------------------
+// MMA1 in the SS form reads 4 KB (A) + 4 KB (B) of shared memory per 64 tensor cycles = the full 128 B/clk smem port, so it
+// cannot run at rate next to the TMA writes.  Here A lives in TMEM (TS form: 64 B/clk) and, TMEM being full (dZ 256 + A 128
+// columns), the S/P buffers shrink to 2 x 64 columns -> column tiles of 64 rows; the freed 64 KB of smem buy 5 TMA stages.
+// TMEM map: [0,256) dZ, [256,384) A (bf16), [384,448) S/P buffer 0, [448,512) S/P buffer 1.
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int nrb, int ntiles,
+                     const float* __restrict__ inv_r /*[>= ntiles*64], zero padded*/, const float* __restrict__ gscale,
+                     const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
+  constexpr int D = NP * kPanelElems;
+  constexpr int kPB = kBwdPanelBytes;                 // 64 rows x 128 B
+  constexpr uint32_t kStageBytes = kPB * kMaxPanels;  // 32 KB
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  uint8_t* sB = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStageBytes * kBwdStages);
+  uint64_t* full = bars;                    // [kBwdStages]
+  uint64_t* empty = full + kBwdStages;      // [kBwdStages]
+  uint64_t* a_full = empty + kBwdStages;    // 4 warp arrivals
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* s_full = a_empty + 1;           // [2]
+  uint64_t* p_full = s_full + 2;            // [2] 8 warp arrivals
+  uint64_t* dz_full = p_full + 2;
+  uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBwdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&p_full[s], 8); }
+    ptx::mbar_init(a_full, 4);
+    ptx::mbar_init(a_empty, 1);
+    ptx::mbar_init(dz_full, 1);
+    ptx::mbar_init(dz_empty, 8);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmap);
+  }
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t tile_bytes = (uint32_t)NP * kPB;
+  constexpr uint32_t kColA = 256u, kColS = 384u;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t sphase = 0;
+      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+        for (int ct = 0; ct < ntiles; ++ct) {
+          ptx::mbar_wait(&empty[stage], sphase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          uint8_t* dst = sB + (size_t)stage * kStageBytes;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBNb);
+          if (++stage == kBwdStages) { stage = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {  // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
+      constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBNb, 0, 0);  // S = A V^T   (A tmem, B K-major)
+      constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);     // dZ += P V   (A tmem, B MN-major)
+      const uint32_t sb0 = ptx::smem_u32(sB);
+      const uint64_t bdesc_k0 = ptx::smem_desc_sw128(sb0, 16, 1024);
+      const uint64_t bdesc_mn0 = ptx::smem_desc_sw128(sb0, kPB, 1024);
+      uint32_t aphase = 0, dzphase = 0;
+      uint32_t tc1 = 0, st1 = 0, ph1 = 0;  // next tile for MMA1: global count, smem stage, stage phase
+      uint32_t tc2 = 0, st2 = 0;           // next tile for MMA2
+      auto issue_mma1 = [&]() {
+        const uint32_t b = tc1 & 1u;
+        ptx::mbar_wait(&full[st1], ph1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + kColS + b * 64u;
+        const uint64_t bd = bdesc_k0 + (uint64_t)(st1 * (kStageBytes >> 4));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < NP * 4; ++kk) {
+            const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
+            ptx::umma_ts(d_tmem, tmem_base + kColA + (uint32_t)kk * 8u, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&s_full[b]);
+        }
+        __syncwarp();
+        ++tc1;
+        if (++st1 == (uint32_t)kBwdStages) { st1 = 0; ph1 ^= 1u; }
+      };
+      auto issue_mma2 = [&](bool first) {
+        const uint32_t b = tc2 & 1u, ph = (tc2 >> 1) & 1u;
+        ptx::mbar_wait(&p_full[b], ph);
+        ptx::tc_fence_after();
+        const uint64_t bmn = bdesc_mn0 + (uint64_t)(st2 * (kStageBytes >> 4));
+        const uint32_t p_tmem = tmem_base + kColS + b * 64u;
+        // K = 64 rows of the V tile, 16 per step; P of columns [32w, 32w+32) sits in TMEM columns [32w, 32w+16)
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBNb / 16; ++k) {
+            ptx::umma_ts(tmem_base, p_tmem + (uint32_t)(k >> 1) * 32u + (uint32_t)(k & 1) * 8u, bmn + (uint32_t)(k * 2048 >> 4), idesc2,
+                         (!first || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[st2]);
+        }
+        __syncwarp();
+        ++tc2;
+        if (++st2 == (uint32_t)kBwdStages) st2 = 0;
+      };
+      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+        ptx::mbar_wait(a_full, aphase);
+        aphase ^= 1;
+        ptx::mbar_wait(dz_empty, dzphase ^ 1);
+        ptx::tc_fence_after();
+        issue_mma1();
+        if (ntiles > 1) issue_mma1();
+        for (int ct = 0; ct < ntiles; ct += 2) {
+          issue_mma2(ct == 0);
+          if (ct + 1 < ntiles) issue_mma2(false);
+          if (ct + 2 < ntiles) issue_mma1();
+          if (ct + 3 < ntiles) issue_mma1();
+        }
+        if (ptx::elect_one()) {
+          ptx::umma_commit(dz_full);
+          ptx::umma_commit(a_empty);
+        }
+        __syncwarp();
+        dzphase ^= 1;
+      }
+    }
+  } else {  // ---------------- softmax / epilogue warpgroups ----------------
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
+    uint32_t tcount = 0, dzphase = 0, aphase = 0;
+    for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      const int row = rb * kBM + lrow;
+      if (wg == 0) {
+        ptx::mbar_wait(a_empty, aphase ^ 1);
+        aphase ^= 1;
+        ptx::tc_fence_after();
+        stage_rows_to_tmem(z, rows, D, row, lane_base + kColA);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full);
+      }
+      const float cu = inv_r[row];  // padded with zeros beyond `rows`
+      const int colbase = wg * 32;
+      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+        const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+        const uint32_t taddr = lane_base + kColS + b * 64u + (uint32_t)colbase;
+        const int gcol0 = ct * kBNb + colbase;  // global column (row of Z) of r[0]
+        const float4* cvp = reinterpret_cast<const float4*>(inv_r + gcol0);
+        float4 cvr[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cvr[q] = __ldg(cvp + q);
+        ptx::mbar_wait(&s_full[b], ph);
+        ptx::tc_fence_after();
+        uint32_t r[32], pk[16];
+        ptx::tmem_ld32(taddr, r);
+        ptx::tmem_ld_wait();
+        const bool diag = (row >= gcol0) && (row < gcol0 + 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 cv = cvr[q];
+          float p0 = ex2(__uint_as_float(r[4 * q + 0])) * (cu + cv.x);
+          float p1 = ex2(__uint_as_float(r[4 * q + 1])) * (cu + cv.y);
+          float p2 = ex2(__uint_as_float(r[4 * q + 2])) * (cu + cv.z);
+          float p3 = ex2(__uint_as_float(r[4 * q + 3])) * (cu + cv.w);
+          if (diag) {
+            const int j = gcol0 + 4 * q;
+            if (j + 0 == row) p0 = 0.f;
+            if (j + 1 == row) p1 = 0.f;
+            if (j + 2 == row) p2 = 0.f;
+            if (j + 3 == row) p3 = 0.f;
+          }
+          pk[2 * q] = pack2(p0, p1);
+          pk[2 * q + 1] = pack2(p2, p3);
+        }
+        ptx::tmem_st16(taddr, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[b]);
+      }
+      ptx::mbar_wait(dz_full, dzphase);
+      dzphase ^= 1;
+      ptx::tc_fence_after();
+      constexpr int half = D / 2;
       const int pair = (row < N) ? row + N : row - N;
       for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
         uint32_t r[32];
@@ -469,13 +797,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Z is [rows, D] bf16 row-major; box = 64 columns (128 B) x 128 rows, 128-byte swizzle, OOB rows read as zero.
-static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D) {
+// Z is [rows, D] bf16 row-major; box = 64 columns (128 B) x box_rows rows, 128-byte swizzle, OOB rows read as zero.
+static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return BMKG_ERR_DRIVER;
   cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kPanelElems, 128u};
+  cuuint32_t box[2] = {(cuuint32_t)kPanelElems, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(z), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -535,17 +863,29 @@ int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* i
   float* block_part = c.take<float>(nb);
 
   CUtensorMap tmap;
-  int rc = make_z_tensormap(&tmap, z_bf16, rows, D);
+  int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
   if (rc != BMKG_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-      return BMKG_ERR_LAUNCH;
-    attr_set = true;
-  }
   const int n_items = s.nrb * s.nchunks;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  infonce_fwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, (int)rows, D / kPanelElems, s, (int)rp, partial);
+  const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
+#define BMKG_LAUNCH_FWD(NP_)                                                                                                      \
+  {                                                                                                                               \
+    static bool attr_set = false;                                                                                                 \
+    if (!attr_set) {                                                                                                              \
+      if (cudaFuncSetAttribute(infonce_fwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes) !=       \
+          cudaSuccess)                                                                                                            \
+        return BMKG_ERR_LAUNCH;                                                                                                   \
+      attr_set = true;                                                                                                            \
+    }                                                                                                                             \
+    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, partial);                    \
+  }
+  switch (D / kPanelElems) {
+    case 1: BMKG_LAUNCH_FWD(1) break;
+    case 2: BMKG_LAUNCH_FWD(2) break;
+    case 3: BMKG_LAUNCH_FWD(3) break;
+    default: BMKG_LAUNCH_FWD(4) break;
+  }
+#undef BMKG_LAUNCH_FWD
   BMKG_CHECK_LAUNCH();
   const float npad = (float)(s.ntiles * kBN - rows);
   infonce_finalize_rows_kernel<<<nb, 256, 0, st>>>(partial, 2 * s.nchunks, (int)rp, (int)rows, (int)N, D, npad,
@@ -562,19 +902,60 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
   BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(inv_r), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = 2 * N;
-  const int nrb = (int)ceil_div(rows, kBM), ntiles = (int)ceil_div(rows, kBN);
-  CUtensorMap tmap;
-  int rc = make_z_tensormap(&tmap, z_bf16, rows, D);
-  if (rc != BMKG_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-      return BMKG_ERR_LAUNCH;
-    attr_set = true;
+  // Two backward variants are kept for A/B measurement (profiles/): the default 128-wide tiles with an SS MMA1 (2.36 ms at
+  // N=28k on B200) and BMKG_INFONCE_BWD=ts64, 64-wide tiles with the stationary block in TMEM (2.50 ms).
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("BMKG_INFONCE_BWD");
+    variant = (e && e[0] == 't') ? 1 : 0;
   }
+  const int bn = variant ? kBNb : kBN;
+  const int nrb = (int)ceil_div(rows, kBM), ntiles = (int)ceil_div(rows, bn);
+  CUtensorMap tmap;
+  int rc = make_z_tensormap(&tmap, z_bf16, rows, D, bn);
+  if (rc != BMKG_OK) return rc;
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
-  infonce_bwd_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmap, (int)rows, (int)N, D, D / kPanelElems, nrb, ntiles, inv_r, gscale,
-                                                         static_cast<const __nv_bfloat16*>(z_bf16), dz);
+  const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
+  if (variant) {
+#define BMKG_LAUNCH_BWD64(NP_)                                                                                                    \
+  {                                                                                                                               \
+    static bool attr_set = false;                                                                                                 \
+    if (!attr_set) {                                                                                                              \
+      if (cudaFuncSetAttribute(infonce_bwd64_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes) !=     \
+          cudaSuccess)                                                                                                            \
+        return BMKG_ERR_LAUNCH;                                                                                                   \
+      attr_set = true;                                                                                                            \
+    }                                                                                                                             \
+    infonce_bwd64_kernel<NP_><<<grid, kThreads, kBwdSmemBytes, st>>>(tmap, (int)rows, (int)N, nrb, ntiles, inv_r, gscale, zp, dz); \
+  }
+    switch (D / kPanelElems) {
+      case 1: BMKG_LAUNCH_BWD64(1) break;
+      case 2: BMKG_LAUNCH_BWD64(2) break;
+      case 3: BMKG_LAUNCH_BWD64(3) break;
+      default: BMKG_LAUNCH_BWD64(4) break;
+    }
+#undef BMKG_LAUNCH_BWD64
+    BMKG_CHECK_LAUNCH();
+    return BMKG_OK;
+  }
+#define BMKG_LAUNCH_BWD(NP_)                                                                                                      \
+  {                                                                                                                               \
+    static bool attr_set = false;                                                                                                 \
+    if (!attr_set) {                                                                                                              \
+      if (cudaFuncSetAttribute(infonce_bwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytesA) !=      \
+          cudaSuccess)                                                                                                            \
+        return BMKG_ERR_LAUNCH;                                                                                                   \
+      attr_set = true;                                                                                                            \
+    }                                                                                                                             \
+    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)rows, (int)N, nrb, ntiles, inv_r, gscale, zp, dz); \
+  }
+  switch (D / kPanelElems) {
+    case 1: BMKG_LAUNCH_BWD(1) break;
+    case 2: BMKG_LAUNCH_BWD(2) break;
+    case 3: BMKG_LAUNCH_BWD(3) break;
+    default: BMKG_LAUNCH_BWD(4) break;
+  }
+#undef BMKG_LAUNCH_BWD
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

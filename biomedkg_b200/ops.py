@@ -179,7 +179,7 @@ def colsum_bf16(x: torch.Tensor, w1=None, w2=None, heads: int = 1):
 
 def _colsum_any(g: torch.Tensor) -> torch.Tensor:
     g = g.contiguous()
-    if g.dtype == BF16 and g.size(1) % 8 == 0 and g.size(1) <= 2048:
+    if g.dtype == BF16 and g.size(1) % 8 == 0:
         return colsum_bf16(g)[0]
     return colsum(g.float())
 
