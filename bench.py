@@ -153,10 +153,17 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     cfg = CONFIGS[args.config]
     N, E, M = cfg["N"], cfg["E"], cfg["M"]
-    x_host, ei_host = synth(cfg, 42 + rank, pin=True)
+    rowshard = args.mode == "rowshard" and world > 1
+    # dp: every rank its own graph (weak scaling, the reference's DDP regime); rowshard: ONE graph on all ranks, the
+    # InfoNCE rows split over the ranks (strong scaling, full-graph loss - SURVEY.md 8e)
+    x_host, ei_host = synth(cfg, 42 if rowshard else 42 + rank, pin=True)
     torch.manual_seed(42)
     mod = b.GRACEModule(IN_DIM, HID, HID, LAYERS, scheduler_type="cosine", learning_rate=1e-3, warm_up_ratio=0.2,
                         fuse_method=cfg["fuse"], encoder=cfg["encoder"]).to(dev).train()
+    if rowshard:
+        from biomedkg_b200.dist import ShardedDualBranchContrast
+
+        mod.contrast_model = ShardedDualBranchContrast(tau=TAU)
     params = [p for p in mod.model.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3)
 
@@ -167,7 +174,7 @@ def run_ours(args, rank, world, local_rank):
         opt.zero_grad(set_to_none=True)
         loss = mod.training_step(batch)
         loss.backward()
-        if world > 1:  # DDP-equivalent: average parameter gradients over ranks (NCCL all-reduce, ~2 MB)
+        if world > 1 and not rowshard:  # DDP-equivalent: average parameter gradients over ranks (NCCL all-reduce, ~2 MB)
             flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
             flat /= world
@@ -193,7 +200,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(res)
     barrier()
-    _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_gcn_aggregate", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+    _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
     _cabi.timings.clear()
     launches0 = _cabi.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -214,7 +221,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = N * world / (ms_max * 1e-3)
+    nodes_total = N if rowshard else N * world
+    value = nodes_total / (ms_max * 1e-3)
     final_loss = float(loss.detach())
 
     # ---------------- end to end: host batch -> loss on host ----------------
@@ -237,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e = {"value": N * world / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8,
+    e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8,
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms}
 
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
@@ -276,9 +284,10 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": "GCL nodes/sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if rowshard else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.config}: {cfg['desc']}", "nodes_per_gpu": N, "edges_per_gpu": E, "modalities": M, "in_dim": IN_DIM,
-                   "hidden": HID, "conv_layers": LAYERS + 2, "tau": TAU, "parallelism": f"dp{world} (per-rank graph, NCCL grad all-reduce)",
+                   "hidden": HID, "conv_layers": LAYERS + 2, "tau": TAU, "parallelism": (f"rowshard{world} (one graph, replicated encoder, InfoNCE rows split over ranks, NCCL all-reduce of 1/R and dZ)"
+                                   if rowshard else f"dp{world} (per-rank graph, NCCL grad all-reduce)"),
                    "l2_policy": "inputs larger than L2 (x is %.0f MB fp32); no explicit flush" % (x_host.numel() * 4 / 1e6),
                    "unused_view": "computed (faithful to model/gcl.py:44)"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
@@ -295,6 +304,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample-nodes", type=int, default=6000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="dp", choices=["dp", "rowshard"], help="multi-GPU mode (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

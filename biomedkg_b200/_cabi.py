@@ -42,8 +42,9 @@ SIGNATURES = {
     "bmkg_edge_sort_workspace_bytes": (SZ, [I64, I64]),
     "bmkg_edge_sort": (I, [P, I64, I64, I, P, P, P, P, P, P, SZ, P]),
     "bmkg_csr_filter_workspace_bytes": (SZ, [I64, I64]),
-    "bmkg_csr_filter": (I, [P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, SZ, P]),
-    "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, P]),
+    "bmkg_csr_filter": (I, [P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, P, SZ, P]),
+    "bmkg_gcn_aggregate_workspace_bytes": (SZ, [I64, I]),
+    "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, I64, P, P, SZ, P]),
     "bmkg_gat_scores": (I, [P, P, P, I64, I, I, P, P, P]),
     "bmkg_gat_aggregate": (I, [P, P, P, P, P, I64, I, I, F, P, I, F, U64, P, P, I, P, P, P]),
     "bmkg_gat_aggregate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, F, P, P, P, P, P]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
     "bmkg_infonce_fwd": (I, [P, I64, I, P, P, P, SZ, P]),
     "bmkg_infonce_bwd": (I, [P, P, P, I64, I, P, P]),
+    "bmkg_infonce_fwd_rows": (I, [P, I64, I, I64, I64, P, P, P, SZ, P]),
+    "bmkg_infonce_bwd_rows": (I, [P, P, P, I64, I, I64, I64, P, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -101,11 +104,11 @@ def bind_thread(device_index: int) -> None:
 #: CUDA kernels each entry point launches per call (for bench.py's gpu_launches count)
 KERNELS_PER_CALL = {
     "bmkg_edge_sort": None,            # data dependent: 3 + 5 * passes + 2 (counted by formula in bench.py)
-    "bmkg_csr_filter": 5, "bmkg_gcn_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
+    "bmkg_csr_filter": 5, "bmkg_gcn_aggregate": 2, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
-    "bmkg_infonce_bwd": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
+    "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
 }
 kernel_launches = 0
 

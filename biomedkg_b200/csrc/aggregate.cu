@@ -17,6 +17,10 @@ namespace bmkg {
 
 constexpr int kAggWarps = 8;
 constexpr int kAggUnroll = 8;
+// Power-law graphs (BASELINE cfg 5): rows longer than kHubThreshold are cut at fixed kHubSeg-edge chunk boundaries of the CSR
+// edge array, each chunk reduced by one CTA into a partial row (8 warps x contiguous sub-ranges, combined in warp order), and
+// the row kernel sums the partials in chunk order.  The split depends only on rowptr, so the result is deterministic; no atomics.
+// (kHubThreshold / kHubSeg live in common.cuh; a chunk intersects at most two hub rows - slot 0: continues, slot 1: starts)
 
 struct AggEpilogue {
   const float* bias;        // [C] or null
@@ -27,27 +31,11 @@ struct AggEpilogue {
   const uint8_t* drop_keep;  // explicit [N,C] keep mask (tests / replay) or null
 };
 
-template <int NV, bool OUT_F32>
-__global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int32_t* __restrict__ rowptr,
-                                                                       const int32_t* __restrict__ colind,
-                                                                       const float* __restrict__ dis,
-                                                                       const __nv_bfloat16* __restrict__ X, int64_t N, int C,
-                                                                       AggEpilogue ep, void* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
-  if (row >= N) return;
-  const int beg = rowptr[row], end = rowptr[row + 1];
-
-  float acc[NV][8];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
-
-  bool act[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) act[v] = (v * 256 + lane * 8) < C;
-
+// acc[v][i] += sum_{k in [beg,end)} dis[colind[k]] * X[colind[k]][v*256 + lane*8 + i]   (CSR order, fp32)
+template <int NV>
+__device__ __forceinline__ void gather_accumulate(const int32_t* __restrict__ colind, const float* __restrict__ dis,
+                                                  const __nv_bfloat16* __restrict__ X, int C, int beg, int end, int lane,
+                                                  const bool (&act)[NV], float (&acc)[NV][8]) {
   for (int base = beg; base < end; base += 32) {
     const int k = base + lane;
     int c = 0;
@@ -87,6 +75,117 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
         }
       }
     }
+  }
+}
+
+// one CTA per kHubSeg-edge chunk of the CSR edge array: partial[(chunk*2 + slot)*C + col] for the hub rows it intersects
+template <int NV>
+__global__ void __launch_bounds__(kAggWarps * 32) gcn_hub_partial_kernel(const int32_t* __restrict__ rowptr,
+                                                                         const int32_t* __restrict__ colind,
+                                                                         const float* __restrict__ dis,
+                                                                         const __nv_bfloat16* __restrict__ X, int64_t N, int C,
+                                                                         const int32_t* __restrict__ hub_rows,
+                                                                         float* __restrict__ partial) {
+  if (hub_rows != nullptr && *hub_rows == 0) return;  // no hub rows in this view: nothing to pre-reduce
+  __shared__ int s_rows[2];         // hub row containing the chunk start (or -1), hub row starting inside (or -1)
+  __shared__ int s_r0, s_r1;
+  extern __shared__ float red[];    // [kAggWarps][C]
+  const int nnz = rowptr[N];
+  const int cs = blockIdx.x * kHubSeg;
+  if (cs >= nnz) return;
+  const int ce = min(cs + kHubSeg, nnz);
+  if (threadIdx.x == 0) {
+    // last row r with rowptr[r] <= x
+    auto row_of = [&](int x) {
+      int lo = 0, hi = (int)N;  // invariant: rowptr[lo] <= x < rowptr[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr[mid] <= x) lo = mid; else hi = mid;
+      }
+      return lo;
+    };
+    s_r0 = row_of(cs);
+    s_r1 = row_of(ce - 1);
+    s_rows[0] = -1;
+    s_rows[1] = -1;
+  }
+  __syncthreads();
+  const int r0 = s_r0, r1 = s_r1;
+  for (int r = r0 + (int)threadIdx.x; r <= r1; r += kAggWarps * 32) {
+    if (rowptr[r + 1] - rowptr[r] > kHubThreshold) s_rows[r == r0 && rowptr[r] < cs ? 0 : 1] = r;  // at most one per slot
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool act[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) act[v] = (v * 256 + lane * 8) < C;
+  for (int slot = 0; slot < 2; ++slot) {
+    const int r = s_rows[slot];
+    if (r < 0) continue;  // uniform across the CTA
+    const int sb = max(rowptr[r], cs), se = min(rowptr[r + 1], ce);
+    const int per = (se - sb + kAggWarps - 1) / kAggWarps;
+    const int wb = min(se, sb + warp * per), we = min(se, wb + per);
+    float acc[NV][8];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+    gather_accumulate<NV>(colind, dis, X, C, wb, we, lane, act, acc);
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (act[v]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[warp * C + v * 256 + lane * 8 + i] = acc[v][i];
+      }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kAggWarps * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAggWarps; ++w) t += red[w * C + c];
+      partial[((int64_t)blockIdx.x * 2 + slot) * C + c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <int NV, bool OUT_F32>
+__global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int32_t* __restrict__ rowptr,
+                                                                       const int32_t* __restrict__ colind,
+                                                                       const float* __restrict__ dis,
+                                                                       const __nv_bfloat16* __restrict__ X, int64_t N, int C,
+                                                                       AggEpilogue ep, const float* __restrict__ hub_partial,
+                                                                       void* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int beg = rowptr[row], end = rowptr[row + 1];
+
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+
+  bool act[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) act[v] = (v * 256 + lane * 8) < C;
+
+  if (hub_partial != nullptr && end - beg > kHubThreshold) {
+    // hub row: sum the per-chunk partial rows in chunk order (slot 1 in the chunk where the row starts, slot 0 after)
+    const int c_first = beg / kHubSeg, c_last = (end - 1) / kHubSeg;
+    for (int c = c_first; c <= c_last; ++c) {
+      const float* pp = hub_partial + ((int64_t)c * 2 + (c == c_first ? 1 : 0)) * C;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (act[v]) {
+          const float4 p0 = *reinterpret_cast<const float4*>(pp + v * 256 + lane * 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(pp + v * 256 + lane * 8 + 4);
+          acc[v][0] += p0.x; acc[v][1] += p0.y; acc[v][2] += p0.z; acc[v][3] += p0.w;
+          acc[v][4] += p1.x; acc[v][5] += p1.y; acc[v][6] += p1.z; acc[v][7] += p1.w;
+        }
+    }
+  } else {
+    gather_accumulate<NV>(colind, dis, X, C, beg, end, lane, act, acc);
   }
 
   const float di = dis[row];
@@ -130,12 +229,18 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
 
 template <int NV>
 static int launch_agg(const int32_t* rowptr, const int32_t* colind, const float* dis, const __nv_bfloat16* X, int64_t N, int C,
-                      const AggEpilogue& ep, void* out, int out_f32, cudaStream_t st) {
+                      const AggEpilogue& ep, void* out, int out_f32, float* hub_partial, const int32_t* hub_rows, int64_t nnz_capacity,
+                      cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(N, kAggWarps);
+  if (hub_partial) {
+    const unsigned chunks = (unsigned)ceil_div(nnz_capacity, kHubSeg);
+    gcn_hub_partial_kernel<NV><<<chunks, kAggWarps * 32, (size_t)kAggWarps * C * sizeof(float), st>>>(rowptr, colind, dis, X, N, C,
+                                                                                                   hub_rows, hub_partial);
+  }
   if (out_f32)
-    gcn_aggregate_kernel<NV, true><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, out);
+    gcn_aggregate_kernel<NV, true><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, out);
   else
-    gcn_aggregate_kernel<NV, false><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, out);
+    gcn_aggregate_kernel<NV, false><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, out);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
@@ -144,9 +249,16 @@ static int launch_agg(const int32_t* rowptr, const int32_t* colind, const float*
 
 using namespace bmkg;
 
+extern "C" size_t bmkg_gcn_aggregate_workspace_bytes(int64_t nnz_capacity, int C) {
+  return (size_t)ceil_div(nnz_capacity > 0 ? nnz_capacity : 1, kHubSeg) * 2 * (size_t)C * sizeof(float);
+}
+
 extern "C" int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* x_bf16, int64_t N,
                                   int C, const float* bias, int relu, float drop_p, uint64_t drop_seed,
-                                  const uint8_t* drop_keep, void* out, int out_is_fp32, void* stream) {
+                                  const uint8_t* drop_keep, void* out, int out_is_fp32, int64_t nnz_capacity,
+                                  const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes, void* stream) {
+  BMKG_REQUIRE(!hub_ws || (nnz_capacity > 0 && hub_ws_bytes >= bmkg_gcn_aggregate_workspace_bytes(nnz_capacity, C)),
+               BMKG_ERR_WORKSPACE);
   BMKG_REQUIRE(rowptr && colind && dis && x_bf16 && out, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && C <= 1024, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(drop_p >= 0.f && drop_p < 1.f, BMKG_ERR_BAD_ARG);
@@ -161,11 +273,12 @@ extern "C" int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, 
   ep.drop_seed = drop_seed;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* X = static_cast<const __nv_bfloat16*>(x_bf16);
+  float* hub = static_cast<float*>(hub_ws);
   const int nv = (C + 255) / 256;
   switch (nv) {
-    case 1: return launch_agg<1>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, st);
-    case 2: return launch_agg<2>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, st);
-    case 3: return launch_agg<3>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, st);
-    default: return launch_agg<4>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, st);
+    case 1: return launch_agg<1>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
+    case 2: return launch_agg<2>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
+    case 3: return launch_agg<3>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
+    default: return launch_agg<4>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
   }
 }

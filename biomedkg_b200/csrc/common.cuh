@@ -26,6 +26,9 @@ namespace bmkg {
 
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200
+// split-row aggregation: rows longer than kHubThreshold edges are reduced chunk-wise (kHubSeg <= kHubThreshold / 2)
+constexpr int kHubThreshold = 1024;
+constexpr int kHubSeg = 512;
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) filter_rows_kernel(const int32_t* __restr
                                                           const int* __restrict__ pos, int64_t N, int64_t E,
                                                           int32_t* __restrict__ rowptr, int32_t* __restrict__ colind,
                                                           int32_t* __restrict__ perm, float* __restrict__ dis,
-                                                          int32_t* __restrict__ nnz_out) {
+                                                          int32_t* __restrict__ nnz_out, int32_t* __restrict__ hub_rows) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int start = pos[rowptr_raw[i]] + (int)i;
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(256) filter_rows_kernel(const int32_t* __restr
   colind[sp] = (int32_t)i;
   if (perm) perm[sp] = pos[E] + (int32_t)i;
   if (dis) dis[i] = 1.0f / sqrtf((float)(end - start));
+  if (hub_rows && end - start > kHubThreshold) atomicAdd(hub_rows, 1);  // integer count: order-independent
   if (i == N - 1) {
     rowptr[N] = end;
     if (nnz_out) *nnz_out = end;
@@ -415,7 +416,7 @@ size_t bmkg_csr_filter_workspace_bytes(int64_t N, int64_t E) {
 int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, const int32_t* perm_sorted,
                     const int32_t* rowptr_raw, const int32_t* selfsplit, const uint8_t* keep, const int64_t* edge_index,
                     int64_t E, int64_t N, int32_t* rowptr, int32_t* colind, int32_t* perm, float* dis, int32_t* nnz_out,
-                    void* ws, size_t ws_bytes, void* stream) {
+                    int32_t* hub_rows_out, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BMKG_REQUIRE(N > 0 && E >= 0 && E + N < (1ll << 31) - 1, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(rowptr_raw && selfsplit && rowptr && colind, BMKG_ERR_BAD_ARG);
@@ -433,8 +434,9 @@ int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, co
     rc = exclusive_scan(OrigFlag{edge_index, edge_index + E, keep}, E, rank, sws, st);
     if (rc != BMKG_OK) return rc;
   }
+  if (hub_rows_out) cudaMemsetAsync(hub_rows_out, 0, sizeof(int32_t), st);
   filter_rows_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(rowptr_raw, selfsplit, pos, N, E, rowptr, colind, perm, dis,
-                                                                  nnz_out);
+                                                                  nnz_out, hub_rows_out);
   if (E > 0)
     filter_edges_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(sf, pos, rank, E, colind, perm);
   BMKG_CHECK_LAUNCH();

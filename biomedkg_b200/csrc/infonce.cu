@@ -54,7 +54,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 struct Schedule {
-  int nrb, ntiles, nchunks, tiles_per_chunk;
+  int rb0, nrb, ntiles, nchunks, tiles_per_chunk;  // row blocks [rb0, rb0 + nrb) of this launch (row-sharded multi-GPU)
 };
 
 // Stationary operand: the calling warp writes 32 rows of Z (one per lane, bf16 pairs packed per 32-bit TMEM column,
@@ -179,7 +179,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
     int tcount = 0;
     uint32_t aphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int rb = item / sch.nchunks, cc = item % sch.nchunks;
+      const int rb = sch.rb0 + item / sch.nchunks, cc = item % sch.nchunks;
       const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
       if (wg == 0) {  // stage this item's 128 stationary rows into TMEM once the previous item's MMAs retired
         ptx::mbar_wait(a_empty, aphase ^ 1);
@@ -241,11 +241,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
 
 // R_u, 1/R_u, ln R_u and the positive-pair logits; fixed-order block partials.
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
-                                                                    int rows, int N, int D, float npad,
+                                                                    int row_begin, int rows, int rows_pad_end, int N, int D, float npad,
                                                                     const __nv_bfloat16* __restrict__ z,
                                                                     float* __restrict__ inv_r, float* __restrict__ block_part) {
   __shared__ float red[8];
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, rows) are this launch's
   float term = 0.f;
   if (u < rows) {
     float R = 0.f;
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
       }
       term -= 2.0f * 0.6931471805599453f * dot;
     }
-  } else if (u < rows_padded) {
+  } else if (u < rows_pad_end) {
     inv_r[u] = 0.f;
   }
   term = warp_sum(term);
@@ -299,7 +299,7 @@ constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int nrb, int ntiles,
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int rb0, int nrb, int ntiles,
                    const float* __restrict__ inv_r /*[>= ntiles*128], zero padded*/, const float* __restrict__ gscale,
                    const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
@@ -350,7 +350,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
     if (lane == 0) {  // ---------------- TMA producer ----------------
       int stage = 0;
       uint32_t sphase = 0, aphase = 0;
-      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_empty, aphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
@@ -393,7 +393,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
         }
         __syncwarp();
       };
-      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::mbar_wait(dz_empty, dzphase ^ 1);
@@ -449,7 +449,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
     uint32_t tcount = 0, dzphase = 0;
-    for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
       const float cu = inv_r[row];  // padded with zeros beyond `rows`
       const int colbase = wg * 64;
@@ -552,7 +552,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
 // TMEM map: [0,256) dZ, [256,384) A (bf16), [384,448) S/P buffer 0, [448,512) S/P buffer 1.
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int nrb, int ntiles,
+infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int rb0, int nrb, int ntiles,
                      const float* __restrict__ inv_r /*[>= ntiles*64], zero padded*/, const float* __restrict__ gscale,
                      const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
@@ -598,7 +598,7 @@ infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, 
     if (lane == 0) {  // ---------------- TMA producer ----------------
       int stage = 0;
       uint32_t sphase = 0;
-      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         for (int ct = 0; ct < ntiles; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
@@ -656,7 +656,7 @@ infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, 
         ++tc2;
         if (++st2 == (uint32_t)kBwdStages) st2 = 0;
       };
-      for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::mbar_wait(dz_empty, dzphase ^ 1);
@@ -684,7 +684,7 @@ infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, 
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
     uint32_t tcount = 0, dzphase = 0, aphase = 0;
-    for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
       if (wg == 0) {
         ptx::mbar_wait(a_empty, aphase ^ 1);
@@ -812,9 +812,10 @@ static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D, 
   return r == CUDA_SUCCESS ? BMKG_OK : BMKG_ERR_DRIVER;
 }
 
-static Schedule make_schedule(int64_t rows) {
+static Schedule make_schedule(int64_t rows, int64_t row_begin, int64_t row_end) {
   Schedule s;
-  s.nrb = (int)ceil_div(rows, kBM);
+  s.rb0 = (int)(row_begin / kBM);
+  s.nrb = (int)ceil_div(row_end - row_begin, kBM);
   s.ntiles = (int)ceil_div(rows, kBN);
   int chunks = (int)ceil_div(2 * kNumSMs, s.nrb);  // aim for >= 2 work items per SM
   if (chunks > s.ntiles) chunks = s.ntiles;
@@ -839,7 +840,7 @@ int64_t bmkg_infonce_padded_rows(int64_t N) { return ceil_div(2 * N, kBN) * kBN;
 size_t bmkg_infonce_workspace_bytes(int64_t N, int D) {
   (void)D;
   const int64_t rows = 2 * N;
-  Schedule s = make_schedule(rows);
+  Schedule s = make_schedule(rows, 0, rows);
   const int64_t rp = bmkg_infonce_padded_rows(N);
   WsCarver c(nullptr);
   c.take<float>((size_t)2 * s.nchunks * rp);
@@ -847,7 +848,12 @@ size_t bmkg_infonce_workspace_bytes(int64_t N, int D) {
   return c.used();
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* inv_r, void* ws, size_t ws_bytes, void* stream) {
+static bool rows_range_ok(int64_t rows, int64_t b, int64_t e) {
+  return b >= 0 && b < e && e <= rows && b % kBM == 0 && (e % kBM == 0 || e == rows);
+}
+
+int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begin, int64_t row_end, float* loss, float* inv_r,
+                          void* ws, size_t ws_bytes, void* stream) {
   BMKG_REQUIRE(z_bf16 && loss && inv_r && N > 0, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
@@ -855,8 +861,9 @@ int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* i
   BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes(N, D), BMKG_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = 2 * N;
+  BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
   const int64_t rp = bmkg_infonce_padded_rows(N);
-  Schedule s = make_schedule(rows);
+  Schedule s = make_schedule(rows, row_begin, row_end);
   WsCarver c(ws);
   float* partial = c.take<float>((size_t)2 * s.nchunks * rp);
   const int nb = (int)ceil_div(rp, 256);
@@ -888,14 +895,22 @@ int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* i
 #undef BMKG_LAUNCH_FWD
   BMKG_CHECK_LAUNCH();
   const float npad = (float)(s.ntiles * kBN - rows);
-  infonce_finalize_rows_kernel<<<nb, 256, 0, st>>>(partial, 2 * s.nchunks, (int)rp, (int)rows, (int)N, D, npad,
-                                                   static_cast<const __nv_bfloat16*>(z_bf16), inv_r, block_part);
-  infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nb, 1.0f / (2.0f * (float)N), loss);
+  // rows of this launch: [row_begin, row_end); the zero padding of inv_r beyond 2N belongs to the launch that owns the last row
+  const int64_t pad_end = (row_end == rows) ? rp : row_end;
+  const int nbr = (int)ceil_div(pad_end - row_begin, 256);
+  infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, 2 * s.nchunks, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
+                                                    D, npad, static_cast<const __nv_bfloat16*>(z_bf16), inv_r, block_part);
+  infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nbr, 1.0f / (2.0f * (float)N), loss);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
 
-int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, float* dz, void* stream) {
+int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* inv_r, void* ws, size_t ws_bytes, void* stream) {
+  return bmkg_infonce_fwd_rows(z_bf16, N, D, 0, 2 * N, loss, inv_r, ws, ws_bytes, stream);
+}
+
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, int64_t row_begin,
+                          int64_t row_end, float* dz, void* stream) {
   BMKG_REQUIRE(z_bf16 && inv_r && gscale && dz && N > 0, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
@@ -909,8 +924,10 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
     const char* e = getenv("BMKG_INFONCE_BWD");
     variant = (e && e[0] == 't') ? 1 : 0;
   }
+  BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
   const int bn = variant ? kBNb : kBN;
-  const int nrb = (int)ceil_div(rows, kBM), ntiles = (int)ceil_div(rows, bn);
+  const int rb0 = (int)(row_begin / kBM);
+  const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, bn);
   CUtensorMap tmap;
   int rc = make_z_tensormap(&tmap, z_bf16, rows, D, bn);
   if (rc != BMKG_OK) return rc;
@@ -926,7 +943,7 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
         return BMKG_ERR_LAUNCH;                                                                                                   \
       attr_set = true;                                                                                                            \
     }                                                                                                                             \
-    infonce_bwd64_kernel<NP_><<<grid, kThreads, kBwdSmemBytes, st>>>(tmap, (int)rows, (int)N, nrb, ntiles, inv_r, gscale, zp, dz); \
+    infonce_bwd64_kernel<NP_><<<grid, kThreads, kBwdSmemBytes, st>>>(tmap, (int)rows, (int)N, rb0, nrb, ntiles, inv_r, gscale, zp, dz); \
   }
     switch (D / kPanelElems) {
       case 1: BMKG_LAUNCH_BWD64(1) break;
@@ -947,7 +964,7 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
         return BMKG_ERR_LAUNCH;                                                                                                   \
       attr_set = true;                                                                                                            \
     }                                                                                                                             \
-    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)rows, (int)N, nrb, ntiles, inv_r, gscale, zp, dz); \
+    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)rows, (int)N, rb0, nrb, ntiles, inv_r, gscale, zp, dz); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_BWD(1) break;
@@ -958,6 +975,10 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
 #undef BMKG_LAUNCH_BWD
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
+}
+
+int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, float* dz, void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, inv_r, gscale, N, D, 0, 2 * N, dz, stream);
 }
 
 }  // extern "C"

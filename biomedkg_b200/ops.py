@@ -103,17 +103,20 @@ class GraphView:
         self.perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
         self.dis = torch.empty(N, dtype=torch.float32, device=dev)
         self.nnz = torch.empty(1, dtype=torch.int32, device=dev)
+        self.hub = torch.empty(2, dtype=torch.int32, device=dev)     # rows longer than the split-row threshold (CSR, CSC)
         s = sg.by[0]
         call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
-             _p(sg.edge_index), E, N, _p(self.rowptr), _p(self.colind), _p(self.perm), _p(self.dis), _p(self.nnz), _p(ws),
-             ws.numel(), _stream())
+             _p(sg.edge_index), E, N, _p(self.rowptr), _p(self.colind), _p(self.perm), _p(self.dis), _p(self.nnz),
+             self.hub.data_ptr(), _p(ws), ws.numel(), _stream())
         self.csc_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
         self.csc_colind = torch.empty(E + N, dtype=torch.int32, device=dev)
         self.csc_perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
         s = sg.by[1]
         call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
-             _p(sg.edge_index), E, N, _p(self.csc_rowptr), _p(self.csc_colind), _p(self.csc_perm), None, None, _p(ws),
-             ws.numel(), _stream())
+             _p(sg.edge_index), E, N, _p(self.csc_rowptr), _p(self.csc_colind), _p(self.csc_perm), None, None,
+             self.hub.data_ptr() + 4, _p(ws), ws.numel(), _stream())
+        self.csr = (self.rowptr, self.colind, self.hub[0:1])
+        self.csc = (self.csc_rowptr, self.csc_colind, self.hub[1:2])
 
 
 _GRAPH_CACHE: dict = {}
@@ -143,15 +146,19 @@ def as_view(graph, num_nodes: int) -> GraphView:
 # ---------------------------------------------------------------------------
 # raw kernel wrappers
 # ---------------------------------------------------------------------------
-def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False):
+def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False,
+                  hub_rows=None):
     _need_cuda(x)
     assert x.dtype == BF16 and x.is_contiguous()
     N, C = x.shape
     out = torch.empty(N, C, dtype=torch.float32 if out_fp32 else BF16, device=x.device)
     if drop_keep is not None:
         drop_keep = drop_keep.contiguous().view(torch.uint8) if drop_keep.dtype == torch.bool else drop_keep.contiguous()
+    cap = int(colind.numel())
+    ws = _ws(lib.bmkg_gcn_aggregate_workspace_bytes(cap, C), x.device)   # split-row partials for hub rows (power-law graphs)
     call("bmkg_gcn_aggregate", _p(rowptr), _p(colind), _p(dis), _p(x), N, C, _p(bias), int(relu), float(drop_p),
-         int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), _stream())
+         int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), cap, _p(hub_rows), _p(ws), ws.numel(),
+         _stream())
     return out
 
 
@@ -292,7 +299,8 @@ class _GCNLayerFn(torch.autograd.Function):
         x = x.contiguous()
         w16 = weight.to(BF16)
         xw = torch.mm(x, w16.t())
-        y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32)
+        y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
+                          hub_rows=view.hub[0:1])
         ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
         ctx.save_for_backward(x, w16, y if relu else None)
         return y
@@ -313,7 +321,7 @@ class _GCNLayerFn(torch.autograd.Function):
         else:
             dbias = colsum(gy.float())
             gpre = gy if gy.dtype == BF16 else gy.to(BF16)
-        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre)
+        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub[1:2])
         dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, None, None, None, None, None, None

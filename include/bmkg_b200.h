@@ -52,22 +52,28 @@ int bmkg_edge_sort(const int64_t* edge_index, int64_t num_edges, int64_t num_nod
  * keep: optional uint8 [E] mask in ORIGINAL edge order (NULL = keep all).  Outputs the canonical CSR
  * of the view's edge list ei' (kept non-self edges in order, then one self-loop per node):
  * rowptr [N+1], colind [E+N capacity], optional perm [E+N] (position in ei'; needs edge_index),
- * optional dis [N] = indegree^-1/2 (fp32), optional nnz_out (device int32). Bit-exact. */
+ * optional dis [N] = indegree^-1/2 (fp32), optional nnz_out (device int32), optional hub_rows_out (device int32: number
+ * of rows longer than 1024 edges, lets the aggregation skip its split-row pre-pass). Bit-exact. */
 size_t bmkg_csr_filter_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, const int32_t* perm_sorted,
                     const int32_t* rowptr_raw, const int32_t* selfsplit, const uint8_t* keep, const int64_t* edge_index,
                     int64_t num_edges, int64_t num_nodes, int32_t* rowptr, int32_t* colind, int32_t* perm, float* dis,
-                    int32_t* nnz_out, void* ws, size_t ws_bytes, void* stream);
+                    int32_t* nnz_out, int32_t* hub_rows_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- A1/A2: GCN aggregation -----------------------------------------------------------------
  * Replaces GCNConv.propagate + bias (+ F.relu, F.dropout of encoder.py:155-158):
  *   out[r] = dropout(relu( dis[r] * sum_{k in row r} dis[colind[k]] * x[colind[k]] + bias ))
  * x bf16 [N,C]; out bf16 or fp32 [N,C]; C % 8 == 0, C <= 1024.  With a CSC graph and no
  * epilogue this is the transposed backward.  drop_keep: optional explicit uint8 [N,C] keep mask,
- * otherwise (drop_p > 0) the counter-based stream hash(drop_seed, r*C+c) decides. */
+ * otherwise (drop_p > 0) the counter-based stream hash(drop_seed, r*C+c) decides.
+ * hub_ws (optional, bmkg_gcn_aggregate_workspace_bytes(nnz_capacity, C) bytes; nnz_capacity = E + N): enables the split-row
+ * path for power-law graphs - rows longer than 1024 edges are reduced chunk-wise by whole CTAs and combined in fixed order;
+ * hub_rows (optional device int32 from bmkg_csr_filter) == 0 skips the pre-pass. */
+size_t bmkg_gcn_aggregate_workspace_bytes(int64_t nnz_capacity, int channels);
 int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* x_bf16, int64_t num_nodes,
                        int channels, const float* bias, int relu, float drop_p, uint64_t drop_seed, const uint8_t* drop_keep,
-                       void* out, int out_is_fp32, void* stream);
+                       void* out, int out_is_fp32, int64_t nnz_capacity, const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes,
+                       void* stream);
 
 /* ---- A3/A4: GAT aggregation (extension - BASELINE.json configs 2 and 5) ---------------------------
  * PyG GATConv(in, out, heads=H, concat=True, negative_slope, add_self_loops=True) semantics;
@@ -148,6 +154,14 @@ int bmkg_infonce_fwd(const void* z_bf16, int64_t num_nodes, int dim, float* loss
                      void* stream);
 int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t num_nodes, int dim, float* dz,
                      void* stream);
+/* Row-sharded variants (multi-GPU): only rows [row_begin, row_end) of the stacked 2N x D matrix are processed
+ * against ALL 2N columns.  row_begin % 128 == 0; row_end % 128 == 0 or row_end == 2N.  fwd_rows writes this range's share
+ * of the loss (the shares of all ranges add up to the loss) and inv_r for the range; bwd_rows needs inv_r for all rows
+ * (all-gathered) and writes dz for the range. */
+int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t num_nodes, int dim, int64_t row_begin, int64_t row_end, float* loss,
+                          float* inv_r, void* ws, size_t ws_bytes, void* stream);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* inv_r, const float* gscale, int64_t num_nodes, int dim,
+                          int64_t row_begin, int64_t row_end, float* dz, void* stream);
 
 #ifdef __cplusplus
 }

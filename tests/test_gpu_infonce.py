@@ -80,3 +80,34 @@ def test_infonce_full_size_cfg2_properties():
     # d loss / d h is orthogonal to h row-wise (loss depends on h only through h/|h|)
     cos = (h1.grad * h1.detach()).sum(1).abs() / (h1.grad.norm(dim=1) * h1.detach().norm(dim=1))
     assert float(cos.max()) < 1e-3
+
+
+@pytest.mark.parametrize("n,d,splits", [(1000, 256, (0, 768, 2000)), (300, 64, (0, 128, 256, 600)), (4096, 256, (0, 4096, 8192))])
+def test_row_sharded_entry_points_compose(n, d, splits):
+    """bmkg_infonce_{fwd,bwd}_rows over disjoint row ranges (what each rank of the row-sharded multi-GPU path runs) add up to
+    the single-launch result: loss shares sum to the loss, 1/R and dZ rows are identical."""
+    from biomedkg_b200 import ops
+    from biomedkg_b200.dist import CudaImpl
+
+    g = torch.Generator().manual_seed(n)
+    h1 = torch.randn(n, d, generator=g).to(DEV)
+    h2 = (h1.cpu() + torch.randn(n, d, generator=g)).to(DEV)
+    impl = CudaImpl()
+    z, inv_norm, scale = impl.prep(h1, h2, 0.2)
+    full_loss, full_inv = impl.fwd_rows(z, n, 0, 2 * n)
+    gs = torch.ones((), device=DEV)
+    full_dz = impl.bwd_rows(z, full_inv, gs, n, 0, 2 * n)
+    loss = torch.zeros((), device=DEV)
+    inv = torch.zeros_like(full_inv)
+    for r0, r1 in zip(splits, splits[1:]):
+        l, i = impl.fwd_rows(z, n, r0, r1)
+        loss += l
+        inv += i
+    assert abs(float(loss) - float(full_loss)) < 1e-6 * abs(float(full_loss))
+    assert torch.equal(inv, full_inv)
+    dz = torch.zeros_like(full_dz)
+    for r0, r1 in zip(splits, splits[1:]):
+        dz += impl.bwd_rows(z, inv, gs, n, r0, r1)
+    assert torch.equal(dz, full_dz)
+    ref = ops.infonce_loss(h1, h2, 0.2)
+    assert abs(float(ref) - float(full_loss)) < 1e-6 * abs(float(ref))

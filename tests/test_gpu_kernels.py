@@ -45,6 +45,34 @@ def test_gcn_aggregate_forward(n, e, c):
     assert rel_err(outT, pyg.gcn_dense_adj(ei, n).t() @ x.double()) < 1e-5
 
 
+def test_gcn_aggregate_hub_rows_split_path():
+    """Power-law shape (BASELINE cfg 5): hub rows longer than 1024 edges take the split-row path (chunk partials combined in
+    fixed order).  Same result as the dense formula, bitwise reproducible, in both CSR and CSC orientation."""
+    from biomedkg_b200 import ops
+
+    n, c = 3000, 256
+    g = torch.Generator().manual_seed(7)
+    hubs = torch.tensor([5, 1700, 2999])
+    deg = [9000, 1025, 30000]                                   # just above the threshold, and spanning many 512-edge chunks
+    src = torch.cat([torch.randint(0, n, (d,), generator=g) for d in deg] + [torch.randint(0, n, (20000,), generator=g)])
+    dst = torch.cat([torch.full((d,), int(h)) for h, d in zip(hubs, deg)] + [torch.randint(0, n, (20000,), generator=g)])
+    ei = torch.stack([src, dst])
+    x = torch.randn(n, c, generator=g).bfloat16()
+    bias = torch.randn(c, generator=g)
+    view = ops.SortedGraph(ei.to(DEV), n).view(None)
+    assert int((view.rowptr[1:] - view.rowptr[:-1]).max()) > 1024 and int(view.hub[0]) == 3 and int(view.hub[1]) == 0
+    A = pyg.gcn_dense_adj(ei, n)
+    out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub[0:1])
+    assert rel_err(out, A @ x.double() + bias.double()) < 1e-5
+    assert torch.equal(out, ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True))
+    outT = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, x.to(DEV), out_fp32=True)   # hubs as sources: short rows
+    assert rel_err(outT, A.t() @ x.double()) < 1e-5
+    view2 = ops.SortedGraph(ei.flip(0).to(DEV), n).view(None)                                        # hubs as sources -> CSC hubs
+    assert int(view2.hub[1]) == 3
+    out2T = ops.gcn_aggregate(view2.csc_rowptr, view2.csc_colind, view2.dis, x.to(DEV), out_fp32=True, hub_rows=view2.hub[1:2])
+    assert rel_err(out2T, pyg.gcn_dense_adj(ei.flip(0), n).t() @ x.double()) < 1e-5
+
+
 def test_gcn_aggregate_hashed_dropout_matches_host_mirror():
     from biomedkg_b200 import ops
     from biomedkg_b200.draws import hash_keep_mask

@@ -29,20 +29,27 @@ if what == "infonce":
     torch.cuda.synchronize()
     f, b = e0.elapsed_time(e1), e1.elapsed_time(e2)
     print(f"N={n} fwd {f:.3f} ms ({6*n*n*256/f/1e9:.0f} TF/s credited)  bwd {b:.3f} ms ({8*n*n*256/b/1e9:.0f} TF/s credited) loss {float(loss):.5f}")
-elif what in ("gcn", "gat"):
+elif what in ("gcn", "gat", "gcn_powerlaw"):
     e = int(sys.argv[4]) if len(sys.argv) > 4 else n * 23
-    ei = torch.randint(0, n, (2, e), device=dev)
+    if what == "gcn_powerlaw":   # destinations ~ Pareto(alpha=2.1) degree sequence, sources uniform (cfg 5)
+        w = (1.0 - torch.rand(n, device=dev, dtype=torch.float64)).pow(-1.0 / 1.1)
+        dst = torch.multinomial((w / w.sum()).float(), e, replacement=True)
+        ei = torch.stack([torch.randint(0, n, (e,), device=dev), dst])
+    else:
+        ei = torch.randint(0, n, (2, e), device=dev)
     view = ops.SortedGraph(ei, n).view(torch.rand(e, device=dev) >= 0.4)
     x = torch.randn(n, 256, device=dev).bfloat16()
     bias = torch.zeros(256, device=dev)
     nnz = int(view.nnz.item())
+    deg = (view.rowptr[1:] - view.rowptr[:-1])
+    print(f"max in-degree {int(deg.max())}, rows with degree > 1024: {int((deg > 1024).sum())}, edges in them {int(deg[deg > 1024].sum())}")
     for _ in range(iters):
-        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1)
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub[0:1])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1)
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub[0:1])
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
