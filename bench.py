@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -193,7 +193,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- device-resident throughput ("value") ----------------
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()                      # started before warm-up so it is already streaming in the timed region
     res = Batch()
     res.x, res.edge_index = x_host.to(dev), ei_host.to(dev)
@@ -305,6 +305,7 @@ def main():
     ap.add_argument("--cpu-sample-nodes", type=int, default=6000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="dp", choices=["dp", "rowshard"], help="multi-GPU mode (N>1)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the run (A/B of its overhead)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -106,10 +106,18 @@ __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restr
   __shared__ float red[8][33];
   const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  float s = 0.f;
-  if (c < C)
-    for (int b = g; b < nb; b += 8) s += partial[(int64_t)b * stride + c];
-  red[g][cl] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // 4 independent chains keep 4 loads in flight; combined in fixed order
+  if (c < C) {
+    int b = g;
+    for (; b + 24 < nb; b += 32) {
+      s0 += partial[(int64_t)b * stride + c];
+      s1 += partial[(int64_t)(b + 8) * stride + c];
+      s2 += partial[(int64_t)(b + 16) * stride + c];
+      s3 += partial[(int64_t)(b + 24) * stride + c];
+    }
+    for (; b < nb; b += 8) s0 += partial[(int64_t)b * stride + c];
+  }
+  red[g][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (g == 0 && c < C) {
     float t = 0.f;

@@ -104,10 +104,10 @@ def test_row_sharded_entry_points_compose(n, d, splits):
         loss += l
         inv += i
     assert abs(float(loss) - float(full_loss)) < 1e-6 * abs(float(full_loss))
-    assert torch.equal(inv, full_inv)
+    assert torch.allclose(inv, full_inv, rtol=2e-6, atol=0)      # column-chunk grouping of the partial sums depends on the range
     dz = torch.zeros_like(full_dz)
     for r0, r1 in zip(splits, splits[1:]):
         dz += impl.bwd_rows(z, inv, gs, n, r0, r1)
-    assert torch.equal(dz, full_dz)
+    assert torch.allclose(dz, full_dz, rtol=1e-4, atol=1e-9)
     ref = ops.infonce_loss(h1, h2, 0.2)
     assert abs(float(ref) - float(full_loss)) < 1e-6 * abs(float(ref))
