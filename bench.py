@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,10 +232,10 @@ def run_ours(args, rank, world, local_rank):
         bt.edge_index = ei_host.to(dev, non_blocking=True)     # a fresh edge_index: the radix sort runs every step
         return float(step(bt).item())                           # device -> host read of the loss
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(2, args.warmup // 2)):
         e2e_step()
     barrier()
-    k2 = max(1, args.steps // 2)
+    k2 = max(1, args.steps)
     e0.record()
     for _ in range(k2):
         e2e_step()
@@ -292,7 +292,28 @@ def run_ours(args, rank, world, local_rank):
                    "unused_view": "computed (faithful to model/gcl.py:44)"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: NCCL / c10d print banners to fd 1, so point fd 1 at stderr for the run and
+    keep a private duplicate for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -312,6 +333,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _protect_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

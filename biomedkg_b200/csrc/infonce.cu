@@ -837,10 +837,16 @@ int bmkg_last_driver_status(void) { return g_last_driver_status; }
 
 int64_t bmkg_infonce_padded_rows(int64_t N) { return ceil_div(2 * N, kBN) * kBN; }
 
-size_t bmkg_infonce_workspace_bytes(int64_t N, int D) {
+static bool rows_range_ok(int64_t rows, int64_t b, int64_t e) {
+  return b >= 0 && b < e && e <= rows && b % kBM == 0 && (e % kBM == 0 || e == rows);
+}
+
+// partial row sums [2 * nchunks][padded rows] + per-CTA loss partials; nchunks depends on how many row blocks the launch owns
+size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int D, int64_t row_begin, int64_t row_end) {
   (void)D;
   const int64_t rows = 2 * N;
-  Schedule s = make_schedule(rows, 0, rows);
+  if (!rows_range_ok(rows, row_begin, row_end)) return 0;
+  Schedule s = make_schedule(rows, row_begin, row_end);
   const int64_t rp = bmkg_infonce_padded_rows(N);
   WsCarver c(nullptr);
   c.take<float>((size_t)2 * s.nchunks * rp);
@@ -848,9 +854,7 @@ size_t bmkg_infonce_workspace_bytes(int64_t N, int D) {
   return c.used();
 }
 
-static bool rows_range_ok(int64_t rows, int64_t b, int64_t e) {
-  return b >= 0 && b < e && e <= rows && b % kBM == 0 && (e % kBM == 0 || e == rows);
-}
+size_t bmkg_infonce_workspace_bytes(int64_t N, int D) { return bmkg_infonce_workspace_bytes_rows(N, D, 0, 2 * N); }
 
 int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begin, int64_t row_end, float* loss, float* inv_r,
                           void* ws, size_t ws_bytes, void* stream) {
@@ -858,10 +862,10 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(aligned16(z_bf16), BMKG_ERR_MISALIGNED);
-  BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes(N, D), BMKG_ERR_WORKSPACE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = 2 * N;
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes_rows(N, D, row_begin, row_end), BMKG_ERR_WORKSPACE);
   const int64_t rp = bmkg_infonce_padded_rows(N);
   Schedule s = make_schedule(rows, row_begin, row_end);
   WsCarver c(ws);

@@ -60,7 +60,7 @@ class CudaImpl:
         loss = torch.zeros((), dtype=torch.float32, device=z.device)
         inv_r = torch.zeros(lib.bmkg_infonce_padded_rows(N), dtype=torch.float32, device=z.device)
         if r1 > r0:
-            ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), z.device)
+            ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, D, r0, r1), z.device)
             call("bmkg_infonce_fwd_rows", _p(z), N, D, r0, r1, _p(loss), _p(inv_r), _p(ws), ws.numel(), _stream())
         return loss, inv_r
 

@@ -158,6 +158,7 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale
  * against ALL 2N columns.  row_begin % 128 == 0; row_end % 128 == 0 or row_end == 2N.  fwd_rows writes this range's share
  * of the loss (the shares of all ranges add up to the loss) and inv_r for the range; bwd_rows needs inv_r for all rows
  * (all-gathered) and writes dz for the range. */
+size_t bmkg_infonce_workspace_bytes_rows(int64_t num_nodes, int dim, int64_t row_begin, int64_t row_end);
 int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t num_nodes, int dim, int64_t row_begin, int64_t row_end, float* loss,
                           float* inv_r, void* ws, size_t ws_bytes, void* stream);
 int bmkg_infonce_bwd_rows(const void* z_bf16, const float* inv_r, const float* gscale, int64_t num_nodes, int dim,
