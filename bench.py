@@ -262,10 +262,20 @@ def run_ours(args, rank, world, local_rank):
     D = HID
     flops_bwd, flops_fwd = 8.0 * N * N * D, 6.0 * N * N * D
     roof = None
+    for k in ("bmkg_infonce_bwd", "bmkg_infonce_fwd"):   # the row-sharded path launches the *_rows entry points
+        if k not in kern_ms and k + "_rows" in kern_ms:
+            kern_ms[k] = kern_ms[k + "_rows"] * world       # per-rank time x ranks = single-GPU-equivalent duration
     if "bmkg_infonce_bwd" in kern_ms:
         ach = flops_bwd / (kern_ms["bmkg_infonce_bwd"] * 1e-3) / 1e12
+        traffic = None   # DRAM bytes per launch from the committed ncu --set full capture, only if it was taken at this N
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["infonce_bwd_kernel"]
+            if tj["N"] == N:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            pass
         roof = {"kernel": "infonce_bwd_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": None, "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": kern_ms["bmkg_infonce_bwd"],
+                "frac": ach / peak_tf, "traffic": traffic, "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": kern_ms["bmkg_infonce_bwd"],
                 "peak_source": peak_src,
                 "also": {"infonce_fwd (3 kernels, 6N^2D)": {"ms": kern_ms.get("bmkg_infonce_fwd"),
                                                          "achieved_tflops": flops_fwd / (kern_ms["bmkg_infonce_fwd"] * 1e-3) / 1e12}}}
