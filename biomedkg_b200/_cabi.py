@@ -46,8 +46,9 @@ SIGNATURES = {
     "bmkg_gcn_aggregate_workspace_bytes": (SZ, [I64, I]),
     "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, I64, P, P, SZ, P]),
     "bmkg_gat_scores": (I, [P, P, P, I64, I, I, P, P, P]),
-    "bmkg_gat_aggregate": (I, [P, P, P, P, P, I64, I, I, F, P, I, F, U64, P, P, I, P, P, P]),
-    "bmkg_gat_aggregate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, F, P, P, P, P, P]),
+    "bmkg_gat_workspace_bytes": (SZ, [I64, I, I]),
+    "bmkg_gat_aggregate": (I, [P, P, P, P, P, I64, I, I, F, P, I, F, U64, P, P, I, P, P, I64, P, P, SZ, P]),
+    "bmkg_gat_aggregate_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I64, I, I, F, P, P, P, P, I64, P, P, P, SZ, P]),
     "bmkg_mask_cast": (I, [P, P, P, I64, P, P, P, P]),
     "bmkg_modality_mean": (I, [P, I64, I, I, P, P, P]),
     "bmkg_colsum_workspace_bytes": (SZ, [I64, I]),
@@ -109,7 +110,7 @@ KERNELS_PER_CALL = {
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
-    "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
+    "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 2, "bmkg_gat_aggregate_bwd": 4, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
 }
 kernel_launches = 0
 

@@ -53,6 +53,9 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # graph indexing
 # ---------------------------------------------------------------------------
+HUB_THRESHOLD = 1024   # csrc/common.cuh kHubThreshold
+
+
 class _Sorted:
     __slots__ = ("major", "minor", "perm", "rowptr_raw", "split")
 
@@ -79,6 +82,14 @@ class SortedGraph:
             call("bmkg_edge_sort", _p(self.edge_index), self.E, self.N, by_src, _p(s.major), _p(s.minor), _p(s.perm),
                  _p(s.rowptr_raw), _p(s.split), _p(ws), ws.numel(), _stream())
             self.by.append(s)
+        # A view only removes edges, so if no raw row (+1 self-loop) exceeds the split-row threshold no view can have hub rows
+        # and the aggregation kernels skip their hub pre-pass launches.  One host read per new edge_index tensor.
+        if self.E > HUB_THRESHOLD:
+            d0 = (self.by[0].rowptr_raw[1:] - self.by[0].rowptr_raw[:-1]).max()
+            d1 = (self.by[1].rowptr_raw[1:] - self.by[1].rowptr_raw[:-1]).max()
+            self.hub_possible = int(torch.maximum(d0, d1).item()) + 1 > HUB_THRESHOLD
+        else:
+            self.hub_possible = False
 
     def view(self, keep: torch.Tensor | None = None, want_perm: bool = False) -> "GraphView":
         return GraphView(self, keep, want_perm)
@@ -97,6 +108,7 @@ class GraphView:
                 raise ValueError("keep mask must have one entry per edge")
             keep = keep.contiguous().view(torch.uint8) if keep.dtype == torch.bool else keep.to(torch.uint8).contiguous()
         self.N, self.cap = N, E + N
+        self.hub_possible = sg.hub_possible
         ws = _ws(lib.bmkg_csr_filter_workspace_bytes(N, E), dev)
         self.rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
         self.colind = torch.empty(E + N, dtype=torch.int32, device=dev)
@@ -155,10 +167,11 @@ def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, dro
     if drop_keep is not None:
         drop_keep = drop_keep.contiguous().view(torch.uint8) if drop_keep.dtype == torch.bool else drop_keep.contiguous()
     cap = int(colind.numel())
-    ws = _ws(lib.bmkg_gcn_aggregate_workspace_bytes(cap, C), x.device)   # split-row partials for hub rows (power-law graphs)
+    # split-row partials for hub rows (power-law graphs); hub_rows=None means "the graph cannot have hub rows": no pre-pass
+    ws = _ws(lib.bmkg_gcn_aggregate_workspace_bytes(cap, C), x.device) if hub_rows is not None else None
     call("bmkg_gcn_aggregate", _p(rowptr), _p(colind), _p(dis), _p(x), N, C, _p(bias), int(relu), float(drop_p),
-         int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), cap, _p(hub_rows), _p(ws), ws.numel(),
-         _stream())
+         int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), cap, _p(hub_rows), _p(ws),
+         ws.numel() if ws is not None else 0, _stream())
     return out
 
 
@@ -300,7 +313,7 @@ class _GCNLayerFn(torch.autograd.Function):
         w16 = weight.to(BF16)
         xw = torch.mm(x, w16.t())
         y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
-                          hub_rows=view.hub[0:1])
+                          hub_rows=view.hub[0:1] if view.hub_possible else None)
         ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
         ctx.save_for_backward(x, w16, y if relu else None)
         return y
@@ -321,7 +334,7 @@ class _GCNLayerFn(torch.autograd.Function):
         else:
             dbias = colsum(gy.float())
             gpre = gy if gy.dtype == BF16 else gy.to(BF16)
-        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub[1:2])
+        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub[1:2] if view.hub_possible else None)
         dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, None, None, None, None, None, None
@@ -359,9 +372,11 @@ class _GATLayerFn(torch.autograd.Function):
         rsum = torch.empty(N, heads, dtype=torch.float32, device=dev)
         keep = _as_u8(drop_keep)
         b = bias.detach().contiguous()
+        cap = int(view.colind.numel())
+        hws = _ws(lib.bmkg_gat_workspace_bytes(cap, heads, C), dev) if view.hub_possible else None   # split-row partials
         call("bmkg_gat_aggregate", _p(view.rowptr), _p(view.colind), _p(xh), _p(a_s), _p(a_d), N, heads, C, float(slope), _p(b),
              int(relu), float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(keep), _p(out), int(out_fp32), _p(rmax), _p(rsum),
-             _stream())
+             cap, view.hub.data_ptr(), _p(hws), hws.numel() if hws is not None else 0, _stream())
         ctx.view, ctx.relu, ctx.drop_p, ctx.heads, ctx.slope = view, relu, drop_p, heads, slope
         ctx.att_shape = att_src.shape
         ctx.save_for_backward(x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, out if relu else None)
@@ -389,9 +404,11 @@ class _GATLayerFn(torch.autograd.Function):
         das = torch.empty(N, H, dtype=torch.float32, device=dev)
         dad = torch.empty(N, H, dtype=torch.float32, device=dev)
         tsum = torch.empty(N, H, dtype=torch.float32, device=dev)
+        cap = int(view.colind.numel())
+        hws = _ws(lib.bmkg_gat_workspace_bytes(cap, H, C), dev) if view.hub_possible else None
         call("bmkg_gat_aggregate_bwd", _p(view.rowptr), _p(view.colind), _p(view.csc_rowptr), _p(view.csc_colind), _p(xh), _p(gpre),
              _p(a_s), _p(a_d), _p(rmax), _p(rsum), _p(atts), _p(attd), N, H, C, float(ctx.slope), _p(dxh), _p(das), _p(dad),
-             _p(tsum), _stream())
+             _p(tsum), cap, view.hub.data_ptr(), view.hub.data_ptr() + 4, _p(hws), hws.numel() if hws is not None else 0, _stream())
         datt_s, datt_d = colsum_bf16(xh, das, dad, H)          # d att_src[h,c] = sum_n d a_src[n,h] xh[n,h,c]
         datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
         dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None

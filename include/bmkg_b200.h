@@ -83,15 +83,20 @@ int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float
  * alpha from node arrays: csr pass -> d_adst, tsum_ws [N,H]; csc pass -> dxh bf16 [N,H*C], d_asrc. */
 int bmkg_gat_scores(const void* xh_bf16, const float* att_src, const float* att_dst, int64_t num_nodes, int heads, int channels,
                     float* a_src, float* a_dst, void* stream);
+/* hub_ws (optional, bmkg_gat_workspace_bytes(nnz_capacity, H, C)) + hub_rows (device int32 counts from bmkg_csr_filter) enable
+ * the split-row path for rows longer than 1024 edges (softmax partials per 512-edge chunk, merged in chunk order). */
+size_t bmkg_gat_workspace_bytes(int64_t nnz_capacity, int heads, int channels);
 int bmkg_gat_aggregate(const int32_t* rowptr, const int32_t* colind, const void* xh_bf16, const float* a_src, const float* a_dst,
                        int64_t num_nodes, int heads, int channels, float negative_slope, const float* bias, int relu,
                        float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, void* out, int out_is_fp32, float* rowmax,
-                       float* rowsum, void* stream);
+                       float* rowsum, int64_t nnz_capacity, const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes,
+                       void* stream);
 int bmkg_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* colind, const int32_t* csc_rowptr, const int32_t* csc_colind,
                            const void* xh_bf16, const void* g_bf16, const float* a_src, const float* a_dst, const float* rowmax,
                            const float* rowsum, const float* att_src, const float* att_dst, int64_t num_nodes, int heads,
                            int channels, float negative_slope, void* dxh_bf16, float* d_asrc, float* d_adst, float* tsum_ws,
-                           void* stream);
+                           int64_t nnz_capacity, const int32_t* hub_rows_csr, const int32_t* hub_rows_csc, void* hub_ws,
+                           size_t hub_ws_bytes, void* stream);
 
 /* ---- elementwise / small reductions -------------------------------------------------------
  * bmkg_mask_cast: torch_geometric.utils.mask_feature(mode="all") (model/gcl.py:40-41,75) fused with the

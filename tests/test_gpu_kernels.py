@@ -64,7 +64,9 @@ def test_gcn_aggregate_hub_rows_split_path():
     A = pyg.gcn_dense_adj(ei, n)
     out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub[0:1])
     assert rel_err(out, A @ x.double() + bias.double()) < 1e-5
-    assert torch.equal(out, ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True))
+    assert torch.equal(out, ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub[0:1]))
+    plain = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True)    # warp-per-row path
+    assert rel_err(out, plain) < 1e-5
     outT = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, x.to(DEV), out_fp32=True)   # hubs as sources: short rows
     assert rel_err(outT, A.t() @ x.double()) < 1e-5
     view2 = ops.SortedGraph(ei.flip(0).to(DEV), n).view(None)                                        # hubs as sources -> CSC hubs
