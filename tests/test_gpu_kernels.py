@@ -208,3 +208,30 @@ def test_attention_fusion_reference_golden(golden_dir):
     red = ReDAF(fx["x"].size(-1)).to(DEV).eval()
     red.load_state_dict(fx["state_dict"])
     assert rel_err(red(fx["x"].to(DEV)), fx["out"]) < 1e-2
+
+
+def test_gcn_aggregate_cfg4_size_vs_torch_sparse():
+    """BASELINE cfg 4 size (130k nodes, 8M edges, one edge-dropped view): the fused CSR aggregation equals a torch fp32 sparse
+    matmul of the same normalised adjacency (plain-PyTorch reference of the same op, on the device), and is linear."""
+    from biomedkg_b200 import ops
+
+    n, e, c = 130_000, 8_000_000, 256
+    g = torch.Generator().manual_seed(4)
+    ei = torch.randint(0, n, (2, e), generator=g, dtype=torch.int64).to(DEV)
+    keep = torch.rand(e, device=DEV) >= 0.4
+    x = torch.randn(n, c, device=DEV).bfloat16()
+    view = ops.sorted_graph(ei, n).view(keep)
+    out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, out_fp32=True)
+    eik = ei[:, keep & (ei[0] != ei[1])]
+    loops = torch.arange(n, device=DEV)
+    row = torch.cat([eik[1], loops])
+    col = torch.cat([eik[0], loops])
+    deg = torch.bincount(row, minlength=n).float()
+    w = deg.pow(-0.5)[row] * deg.pow(-0.5)[col]
+    A = torch.sparse_coo_tensor(torch.stack([row, col]), w, (n, n)).coalesce()
+    ref = torch.sparse.mm(A, x.float())
+    assert rel_err(out, ref) < 1e-5
+    y = torch.randn(n, c, device=DEV).bfloat16()
+    out_y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, y, out_fp32=True)
+    out_xy = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, (x.float() + y.float()).bfloat16(), out_fp32=True)
+    assert rel_err(out_xy, out + out_y) < 5e-3            # linearity up to the bf16 rounding of x + y
