@@ -13,7 +13,7 @@ import torch
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libbmkg_b200.so")
+LIB_PATH = os.environ.get("BMKG_LIB_PATH") or os.path.join(_HERE, "_lib", "libbmkg_b200.so")   # env override: tuning builds
 
 
 class BmkgError(RuntimeError):
@@ -42,6 +42,7 @@ SIGNATURES = {
     "bmkg_edge_sort_workspace_bytes": (SZ, [I64, I64]),
     "bmkg_edge_sort": (I, [P, I64, I64, I, P, P, P, P, P, P, SZ, P]),
     "bmkg_csr_filter_workspace_bytes": (SZ, [I64, I64]),
+    "bmkg_hub_info_len": (I64, [I64, I64]),
     "bmkg_csr_filter": (I, [P, P, P, P, P, P, P, I64, I64, P, P, P, P, P, P, P, SZ, P]),
     "bmkg_gcn_aggregate_workspace_bytes": (SZ, [I64, I]),
     "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, I64, P, P, SZ, P]),
@@ -107,7 +108,7 @@ def bind_thread(device_index: int) -> None:
 #: pre-passes of the aggregation kernels are not counted - a lower bound)
 KERNELS_PER_CALL = {
     "bmkg_edge_sort": None,            # data dependent: 3 + 5 * passes + 2 (counted by formula in bench.py)
-    "bmkg_csr_filter": 5, "bmkg_gcn_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
+    "bmkg_csr_filter": 6, "bmkg_gcn_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,

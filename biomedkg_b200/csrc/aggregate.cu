@@ -84,37 +84,12 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_hub_partial_kernel(const i
                                                                          const int32_t* __restrict__ colind,
                                                                          const float* __restrict__ dis,
                                                                          const __nv_bfloat16* __restrict__ X, int64_t N, int C,
-                                                                         const int32_t* __restrict__ hub_rows,
+                                                                         const int32_t* __restrict__ hub_rows /*hub_info*/,
                                                                          float* __restrict__ partial) {
-  if (hub_rows != nullptr && *hub_rows == 0) return;  // no hub rows in this view: nothing to pre-reduce
   __shared__ int s_rows[2];         // hub row containing the chunk start (or -1), hub row starting inside (or -1)
-  __shared__ int s_r0, s_r1;
   extern __shared__ float red[];    // [kAggWarps][C]
-  const int nnz = rowptr[N];
-  const int cs = blockIdx.x * kHubSeg;
-  if (cs >= nnz) return;
-  const int ce = min(cs + kHubSeg, nnz);
-  if (threadIdx.x == 0) {
-    // last row r with rowptr[r] <= x
-    auto row_of = [&](int x) {
-      int lo = 0, hi = (int)N;  // invariant: rowptr[lo] <= x < rowptr[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (rowptr[mid] <= x) lo = mid; else hi = mid;
-      }
-      return lo;
-    };
-    s_r0 = row_of(cs);
-    s_r1 = row_of(ce - 1);
-    s_rows[0] = -1;
-    s_rows[1] = -1;
-  }
-  __syncthreads();
-  const int r0 = s_r0, r1 = s_r1;
-  for (int r = r0 + (int)threadIdx.x; r <= r1; r += kAggWarps * 32) {
-    if (rowptr[r + 1] - rowptr[r] > kHubThreshold) s_rows[r == r0 && rowptr[r] < cs ? 0 : 1] = r;  // at most one per slot
-  }
-  __syncthreads();
+  int cs, ce;
+  if (!hub_chunk_rows(rowptr, N, hub_rows, s_rows, cs, ce)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool act[NV];
 #pragma unroll

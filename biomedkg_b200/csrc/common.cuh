@@ -27,8 +27,13 @@ namespace bmkg {
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200
 // split-row aggregation: rows longer than kHubThreshold edges are reduced chunk-wise (kHubSeg <= kHubThreshold / 2)
-constexpr int kHubThreshold = 1024;
-constexpr int kHubSeg = 512;
+#ifndef BMKG_HUB_THRESHOLD
+#define BMKG_HUB_THRESHOLD 1024
+#define BMKG_HUB_SEG 512
+#endif
+constexpr int kHubThreshold = BMKG_HUB_THRESHOLD;
+constexpr int kHubSeg = BMKG_HUB_SEG;
+static_assert(kHubSeg * 2 <= kHubThreshold, "a chunk may meet at most two hub rows");
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -58,6 +63,29 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Split-row pre-pass set-up shared by the GCN / GAT hub kernels.  hub_info = [#hub rows | first row of chunk 0 | chunk 1 | ...]
+// (written by bmkg_csr_filter).  Finds the (at most two) hub rows the chunk blockIdx.x meets: s_rows[0] = the one continuing
+// into the chunk, s_rows[1] = the one starting inside it.  Returns false when the CTA has nothing to do.
+__device__ __forceinline__ bool hub_chunk_rows(const int32_t* __restrict__ rowptr, int64_t N, const int32_t* __restrict__ hub_info,
+                                               int* s_rows, int& cs, int& ce) {
+  if (hub_info == nullptr || hub_info[0] == 0) return false;
+  const int r0 = hub_info[1 + blockIdx.x];
+  if (r0 < 0) return false;
+  const int nnz = rowptr[N];
+  cs = blockIdx.x * kHubSeg;
+  ce = min(cs + kHubSeg, nnz);
+  const int nxt = (ce < nnz) ? hub_info[2 + blockIdx.x] : (int)N - 1;   // row holding the next chunk's first edge
+  const int r1 = nxt < 0 ? (int)N - 1 : nxt;
+  if (threadIdx.x == 0) { s_rows[0] = -1; s_rows[1] = -1; }
+  __syncthreads();
+  for (int r = r0 + (int)threadIdx.x; r <= r1; r += blockDim.x) {
+    const int b = rowptr[r], e = rowptr[r + 1];
+    if (e - b > kHubThreshold && b < ce && e > cs) s_rows[(b < cs) ? 0 : 1] = r;   // at most one row per slot
+  }
+  __syncthreads();
+  return (s_rows[0] >= 0) || (s_rows[1] >= 0);
 }
 
 // 8 bf16 packed in a uint4 <-> 8 floats

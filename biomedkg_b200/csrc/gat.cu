@@ -71,40 +71,6 @@ struct GatEpilogue {
 // Hub rows (power-law graphs, BASELINE cfg 5) use the same fixed chunking of the CSR edge array as the GCN kernel
 // (common.cuh: kHubThreshold / kHubSeg): one CTA per chunk pre-reduces the hub rows it meets - for the softmax that is a
 // (max, sum, weighted row) triple per (chunk, slot), merged in chunk order with the usual exp(max_c - max) rescale.
-struct HubCtx {
-  int r0, r1;       // rows containing the first / last edge of the chunk
-  int rows[2];      // hub row continuing into the chunk (slot 0) / starting inside it (slot 1), or -1
-};
-
-__device__ __forceinline__ bool hub_chunk_setup(const int32_t* __restrict__ rowptr, int64_t N, const int32_t* __restrict__ hub_rows,
-                                                int* s_rows, int* s_r, int& cs, int& ce) {
-  if (hub_rows != nullptr && *hub_rows == 0) return false;
-  const int nnz = rowptr[N];
-  cs = blockIdx.x * kHubSeg;
-  if (cs >= nnz) return false;
-  ce = min(cs + kHubSeg, nnz);
-  if (threadIdx.x == 0) {
-    auto row_of = [&](int x) {  // last row r with rowptr[r] <= x
-      int lo = 0, hi = (int)N;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (rowptr[mid] <= x) lo = mid; else hi = mid;
-      }
-      return lo;
-    };
-    s_r[0] = row_of(cs);
-    s_r[1] = row_of(ce - 1);
-    s_rows[0] = -1;
-    s_rows[1] = -1;
-  }
-  __syncthreads();
-  const int r0 = s_r[0], r1 = s_r[1];
-  for (int r = r0 + (int)threadIdx.x; r <= r1; r += blockDim.x)
-    if (rowptr[r + 1] - rowptr[r] > kHubThreshold) s_rows[(r == r0 && rowptr[r] < cs) ? 0 : 1] = r;
-  __syncthreads();
-  return true;
-}
-
 // softmax statistics and weighted row sum of the edges [beg, end) of one destination row (whole warp)
 template <int H, int NV>
 __device__ __forceinline__ void gat_fwd_segment(const int32_t* __restrict__ colind, const __nv_bfloat16* __restrict__ xh,
@@ -188,11 +154,11 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_hub_fwd_kernel(const int32
                                                                      const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                                      int64_t N, int C, float slope, const int32_t* __restrict__ hub_rows,
                                                                      float* __restrict__ pacc, float* __restrict__ pstat) {
-  __shared__ int s_rows[2], s_r[2];
+  __shared__ int s_rows[2];
   __shared__ float s_m[kGatWarps][H], s_s[kGatWarps][H];
   extern __shared__ float red[];  // [kGatWarps][HC]
   int cs, ce;
-  if (!hub_chunk_setup(rowptr, N, hub_rows, s_rows, s_r, cs, ce)) return;
+  if (!hub_chunk_rows(rowptr, N, hub_rows, s_rows, cs, ce)) return;
   const int HC = H * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int hl[NV];
@@ -416,10 +382,10 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_hub_bwd_dst_kernel(const i
                                                                          const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                                                                          int64_t N, int C, float slope, const int32_t* __restrict__ hub_rows,
                                                                          float* __restrict__ pabt) {
-  __shared__ int s_rows[2], s_r[2];
+  __shared__ int s_rows[2];
   __shared__ float s_abt[kGatWarps][3 * H];
   int cs, ce;
-  if (!hub_chunk_setup(rowptr, N, hub_rows, s_rows, s_r, cs, ce)) return;
+  if (!hub_chunk_rows(rowptr, N, hub_rows, s_rows, cs, ce)) return;
   const int HC = H * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int hl[NV];
@@ -565,11 +531,11 @@ __global__ void __launch_bounds__(kGatWarps * 32) gat_hub_bwd_src_kernel(const i
                                                                          const float* __restrict__ tsum, int64_t N, int C, float slope,
                                                                          const int32_t* __restrict__ hub_rows, float* __restrict__ pacc,
                                                                          float* __restrict__ pdas) {
-  __shared__ int s_rows[2], s_r[2];
+  __shared__ int s_rows[2];
   __shared__ float s_das[kGatWarps][H];
   extern __shared__ float red[];  // [kGatWarps][HC]
   int cs, ce;
-  if (!hub_chunk_setup(csc_rowptr, N, hub_rows, s_rows, s_r, cs, ce)) return;
+  if (!hub_chunk_rows(csc_rowptr, N, hub_rows, s_rows, cs, ce)) return;
   const int HC = H * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int hl[NV];

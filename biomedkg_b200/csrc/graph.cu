@@ -331,6 +331,22 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(SortedFlag flag, cons
   if (perm) perm[o] = rank_orig[flag.perm[k]];
 }
 
+// hub_info[1 + c] = row that contains edge c * kHubSeg of the view's CSR (or -1 past the end): lets the split-row pre-pass of the
+// aggregation kernels find its rows without a serial binary search per CTA
+__global__ void __launch_bounds__(256) chunk_rows_kernel(const int32_t* __restrict__ rowptr, int64_t N, int nchunks,
+                                                         int32_t* __restrict__ hub_info) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const int x = c * kHubSeg;
+  if (x >= rowptr[N]) { hub_info[1 + c] = -1; return; }
+  int lo = 0, hi = (int)N;  // last row r with rowptr[r] <= x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] <= x) lo = mid; else hi = mid;
+  }
+  hub_info[1 + c] = lo;
+}
+
 __global__ void empty_graph_kernel(int64_t N, int32_t* rowptr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= N) rowptr[i] = 0;
@@ -439,8 +455,14 @@ int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, co
                                                                   nnz_out, hub_rows_out);
   if (E > 0)
     filter_edges_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(sf, pos, rank, E, colind, perm);
+  if (hub_rows_out) {
+    const int nchunks = (int)ceil_div(E + N, kHubSeg);
+    chunk_rows_kernel<<<(unsigned)ceil_div(nchunks, 256), 256, 0, st>>>(rowptr, N, nchunks, hub_rows_out);
+  }
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
+
+int64_t bmkg_hub_info_len(int64_t N, int64_t E) { return 1 + ceil_div(E + N, kHubSeg); }
 
 }  // extern "C"

@@ -53,7 +53,9 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # graph indexing
 # ---------------------------------------------------------------------------
-HUB_THRESHOLD = 1024   # csrc/common.cuh kHubThreshold
+import os as _os
+
+HUB_THRESHOLD = int(_os.environ.get("BMKG_HUB_THRESHOLD", "1024"))   # csrc/common.cuh kHubThreshold (env only for tuning builds)
 
 
 class _Sorted:
@@ -115,20 +117,25 @@ class GraphView:
         self.perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
         self.dis = torch.empty(N, dtype=torch.float32, device=dev)
         self.nnz = torch.empty(1, dtype=torch.int32, device=dev)
-        self.hub = torch.empty(2, dtype=torch.int32, device=dev)     # rows longer than the split-row threshold (CSR, CSC)
+        hl = int(lib.bmkg_hub_info_len(N, E))                        # [#hub rows | first row of every 512-edge chunk], CSR then CSC
+        self.hub_info = torch.empty(2, hl, dtype=torch.int32, device=dev)
         s = sg.by[0]
         call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
              _p(sg.edge_index), E, N, _p(self.rowptr), _p(self.colind), _p(self.perm), _p(self.dis), _p(self.nnz),
-             self.hub.data_ptr(), _p(ws), ws.numel(), _stream())
+             _p(self.hub_info[0]), _p(ws), ws.numel(), _stream())
         self.csc_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
         self.csc_colind = torch.empty(E + N, dtype=torch.int32, device=dev)
         self.csc_perm = torch.empty(E + N, dtype=torch.int32, device=dev) if want_perm else None
         s = sg.by[1]
         call("bmkg_csr_filter", _p(s.major), _p(s.minor), _p(s.perm), _p(s.rowptr_raw), _p(s.split), _p(keep),
              _p(sg.edge_index), E, N, _p(self.csc_rowptr), _p(self.csc_colind), _p(self.csc_perm), None, None,
-             self.hub.data_ptr() + 4, _p(ws), ws.numel(), _stream())
-        self.csr = (self.rowptr, self.colind, self.hub[0:1])
-        self.csc = (self.csc_rowptr, self.csc_colind, self.hub[1:2])
+             _p(self.hub_info[1]), _p(ws), ws.numel(), _stream())
+        self.hub_csr, self.hub_csc = self.hub_info[0], self.hub_info[1]
+
+    @property
+    def hub(self):
+        """number of hub rows (CSR, CSC) - int32 [2] device tensor"""
+        return self.hub_info[:, 0]
 
 
 _GRAPH_CACHE: dict = {}
@@ -313,7 +320,7 @@ class _GCNLayerFn(torch.autograd.Function):
         w16 = weight.to(BF16)
         xw = torch.mm(x, w16.t())
         y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
-                          hub_rows=view.hub[0:1] if view.hub_possible else None)
+                          hub_rows=view.hub_csr if view.hub_possible else None)
         ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
         ctx.save_for_backward(x, w16, y if relu else None)
         return y
@@ -334,7 +341,7 @@ class _GCNLayerFn(torch.autograd.Function):
         else:
             dbias = colsum(gy.float())
             gpre = gy if gy.dtype == BF16 else gy.to(BF16)
-        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub[1:2] if view.hub_possible else None)
+        dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub_csc if view.hub_possible else None)
         dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, None, None, None, None, None, None
@@ -376,7 +383,7 @@ class _GATLayerFn(torch.autograd.Function):
         hws = _ws(lib.bmkg_gat_workspace_bytes(cap, heads, C), dev) if view.hub_possible else None   # split-row partials
         call("bmkg_gat_aggregate", _p(view.rowptr), _p(view.colind), _p(xh), _p(a_s), _p(a_d), N, heads, C, float(slope), _p(b),
              int(relu), float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(keep), _p(out), int(out_fp32), _p(rmax), _p(rsum),
-             cap, view.hub.data_ptr(), _p(hws), hws.numel() if hws is not None else 0, _stream())
+             cap, _p(view.hub_csr), _p(hws), hws.numel() if hws is not None else 0, _stream())
         ctx.view, ctx.relu, ctx.drop_p, ctx.heads, ctx.slope = view, relu, drop_p, heads, slope
         ctx.att_shape = att_src.shape
         ctx.save_for_backward(x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, out if relu else None)
@@ -408,7 +415,7 @@ class _GATLayerFn(torch.autograd.Function):
         hws = _ws(lib.bmkg_gat_workspace_bytes(cap, H, C), dev) if view.hub_possible else None
         call("bmkg_gat_aggregate_bwd", _p(view.rowptr), _p(view.colind), _p(view.csc_rowptr), _p(view.csc_colind), _p(xh), _p(gpre),
              _p(a_s), _p(a_d), _p(rmax), _p(rsum), _p(atts), _p(attd), N, H, C, float(ctx.slope), _p(dxh), _p(das), _p(dad),
-             _p(tsum), cap, view.hub.data_ptr(), view.hub.data_ptr() + 4, _p(hws), hws.numel() if hws is not None else 0, _stream())
+             _p(tsum), cap, _p(view.hub_csr), _p(view.hub_csc), _p(hws), hws.numel() if hws is not None else 0, _stream())
         datt_s, datt_d = colsum_bf16(xh, das, dad, H)          # d att_src[h,c] = sum_n d a_src[n,h] xh[n,h,c]
         datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
         dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None

@@ -52,8 +52,10 @@ int bmkg_edge_sort(const int64_t* edge_index, int64_t num_edges, int64_t num_nod
  * keep: optional uint8 [E] mask in ORIGINAL edge order (NULL = keep all).  Outputs the canonical CSR
  * of the view's edge list ei' (kept non-self edges in order, then one self-loop per node):
  * rowptr [N+1], colind [E+N capacity], optional perm [E+N] (position in ei'; needs edge_index),
- * optional dis [N] = indegree^-1/2 (fp32), optional nnz_out (device int32), optional hub_rows_out (device int32: number
- * of rows longer than 1024 edges, lets the aggregation skip its split-row pre-pass). Bit-exact. */
+ * optional dis [N] = indegree^-1/2 (fp32), optional nnz_out (device int32), optional hub_rows_out = "hub info" (device int32
+ * [bmkg_hub_info_len(N,E)]: [0] = number of rows longer than 1024 edges, [1+c] = row holding edge 512*c) which the aggregation
+ * kernels take as `hub_rows` to run (or skip) their split-row pre-pass. Bit-exact. */
+int64_t bmkg_hub_info_len(int64_t num_nodes, int64_t num_edges);
 size_t bmkg_csr_filter_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, const int32_t* perm_sorted,
                     const int32_t* rowptr_raw, const int32_t* selfsplit, const uint8_t* keep, const int64_t* edge_index,

@@ -62,16 +62,16 @@ def test_gcn_aggregate_hub_rows_split_path():
     view = ops.SortedGraph(ei.to(DEV), n).view(None)
     assert int((view.rowptr[1:] - view.rowptr[:-1]).max()) > 1024 and int(view.hub[0]) == 3 and int(view.hub[1]) == 0
     A = pyg.gcn_dense_adj(ei, n)
-    out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub[0:1])
+    out = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub_csr)
     assert rel_err(out, A @ x.double() + bias.double()) < 1e-5
-    assert torch.equal(out, ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub[0:1]))
+    assert torch.equal(out, ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True, hub_rows=view.hub_csr))
     plain = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x.to(DEV), bias.to(DEV), out_fp32=True)    # warp-per-row path
     assert rel_err(out, plain) < 1e-5
     outT = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, x.to(DEV), out_fp32=True)   # hubs as sources: short rows
     assert rel_err(outT, A.t() @ x.double()) < 1e-5
     view2 = ops.SortedGraph(ei.flip(0).to(DEV), n).view(None)                                        # hubs as sources -> CSC hubs
     assert int(view2.hub[1]) == 3
-    out2T = ops.gcn_aggregate(view2.csc_rowptr, view2.csc_colind, view2.dis, x.to(DEV), out_fp32=True, hub_rows=view2.hub[1:2])
+    out2T = ops.gcn_aggregate(view2.csc_rowptr, view2.csc_colind, view2.dis, x.to(DEV), out_fp32=True, hub_rows=view2.hub_csc)
     assert rel_err(out2T, pyg.gcn_dense_adj(ei.flip(0), n).t() @ x.double()) < 1e-5
 
 

@@ -44,12 +44,12 @@ elif what in ("gcn", "gat", "gcn_powerlaw"):
     deg = (view.rowptr[1:] - view.rowptr[:-1])
     print(f"max in-degree {int(deg.max())}, rows with degree > 1024: {int((deg > 1024).sum())}, edges in them {int(deg[deg > 1024].sum())}")
     for _ in range(iters):
-        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub[0:1])
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub_csr)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub[0:1])
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, relu=True, drop_p=0.2, drop_seed=1, hub_rows=view.hub_csr)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
