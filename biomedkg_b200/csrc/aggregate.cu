@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_hub_partial_kernel(const i
                                                                          const float* __restrict__ dis,
                                                                          const __nv_bfloat16* __restrict__ X, int64_t N, int C,
                                                                          const int32_t* __restrict__ hub_rows /*hub_info*/,
-                                                                         float* __restrict__ partial) {
+                                                                         int64_t row_begin, int64_t row_end, float* __restrict__ partial) {
   __shared__ int s_rows[2];         // hub row containing the chunk start (or -1), hub row starting inside (or -1)
   extern __shared__ float red[];    // [kAggWarps][C]
   int cs, ce;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_hub_partial_kernel(const i
   for (int v = 0; v < NV; ++v) act[v] = (v * 256 + lane * 8) < C;
   for (int slot = 0; slot < 2; ++slot) {
     const int r = s_rows[slot];
-    if (r < 0) continue;  // uniform across the CTA
+    if (r < 0 || r < row_begin || r >= row_end) continue;  // uniform across the CTA; rows of other ranks are not ours to reduce
     const int sb = max(rowptr[r], cs), se = min(rowptr[r + 1], ce);
     const int per = (se - sb + kAggWarps - 1) / kAggWarps;
     const int wb = min(se, sb + warp * per), we = min(se, wb + per);
@@ -129,10 +129,13 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
                                                                        const float* __restrict__ dis,
                                                                        const __nv_bfloat16* __restrict__ X, int64_t N, int C,
                                                                        AggEpilogue ep, const float* __restrict__ hub_partial,
-                                                                       void* __restrict__ out) {
+                                                                       int64_t row_begin, void* __restrict__ out) {
+  // rows [row_begin, row_begin + N) of the graph; `out` (and an explicit dropout mask) hold those N rows only: the row-sharded
+  // multi-GPU encoder aggregates its own destination rows from the all-gathered X
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
-  if (row >= N) return;
+  const int64_t lrow = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+  if (lrow >= N) return;
+  const int64_t row = row_begin + lrow;
   const int beg = rowptr[row], end = rowptr[row + 1];
 
   float acc[NV][8];
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
       for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
     }
     if (ep.drop_keep) {
-      const uint2 m = *reinterpret_cast<const uint2*>(ep.drop_keep + row * C + c0);
+      const uint2 m = *reinterpret_cast<const uint2*>(ep.drop_keep + lrow * C + c0);
       const uint32_t mm[2] = {m.x, m.y};
 #pragma unroll
       for (int i = 0; i < 8; ++i) r[i] = ((mm[i >> 2] >> (8 * (i & 3))) & 0xff) ? r[i] * ep.drop_scale : 0.f;
@@ -192,11 +195,11 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
         r[i] = hash_keep(ep.drop_seed, (uint64_t)(row * C + c0 + i), ep.drop_threshold) ? r[i] * ep.drop_scale : 0.f;
     }
     if (OUT_F32) {
-      float* o = static_cast<float*>(out) + row * C + c0;
+      float* o = static_cast<float*>(out) + lrow * C + c0;
       *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
     } else {
-      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + row * C + c0;
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + lrow * C + c0;
       *reinterpret_cast<uint4*>(o) = pack8(r);
     }
   }
@@ -205,17 +208,17 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
 template <int NV>
 static int launch_agg(const int32_t* rowptr, const int32_t* colind, const float* dis, const __nv_bfloat16* X, int64_t N, int C,
                       const AggEpilogue& ep, void* out, int out_f32, float* hub_partial, const int32_t* hub_rows, int64_t nnz_capacity,
-                      cudaStream_t st) {
+                      int64_t row_begin, int64_t total_rows, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(N, kAggWarps);
   if (hub_partial) {
     const unsigned chunks = (unsigned)ceil_div(nnz_capacity, kHubSeg);
-    gcn_hub_partial_kernel<NV><<<chunks, kAggWarps * 32, (size_t)kAggWarps * C * sizeof(float), st>>>(rowptr, colind, dis, X, N, C,
-                                                                                                   hub_rows, hub_partial);
+    gcn_hub_partial_kernel<NV><<<chunks, kAggWarps * 32, (size_t)kAggWarps * C * sizeof(float), st>>>(
+        rowptr, colind, dis, X, total_rows, C, hub_rows, row_begin, row_begin + N, hub_partial);
   }
   if (out_f32)
-    gcn_aggregate_kernel<NV, true><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, out);
+    gcn_aggregate_kernel<NV, true><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, row_begin, out);
   else
-    gcn_aggregate_kernel<NV, false><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, out);
+    gcn_aggregate_kernel<NV, false><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, X, N, C, ep, hub_partial, row_begin, out);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
@@ -232,6 +235,16 @@ extern "C" int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, 
                                   int C, const float* bias, int relu, float drop_p, uint64_t drop_seed,
                                   const uint8_t* drop_keep, void* out, int out_is_fp32, int64_t nnz_capacity,
                                   const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes, void* stream) {
+  return bmkg_gcn_aggregate_rows(rowptr, colind, dis, x_bf16, N, 0, N, C, bias, relu, drop_p, drop_seed, drop_keep, out, out_is_fp32,
+                                 nnz_capacity, hub_rows, hub_ws, hub_ws_bytes, stream);
+}
+
+extern "C" int bmkg_gcn_aggregate_rows(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* x_bf16,
+                                       int64_t total_rows, int64_t row_begin, int64_t N, int C, const float* bias, int relu,
+                                       float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, void* out, int out_is_fp32,
+                                       int64_t nnz_capacity, const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes,
+                                       void* stream) {
+  BMKG_REQUIRE(row_begin >= 0 && N > 0 && row_begin + N <= total_rows, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(!hub_ws || (nnz_capacity > 0 && hub_ws_bytes >= bmkg_gcn_aggregate_workspace_bytes(nnz_capacity, C)),
                BMKG_ERR_WORKSPACE);
   BMKG_REQUIRE(rowptr && colind && dis && x_bf16 && out, BMKG_ERR_BAD_ARG);
@@ -251,9 +264,9 @@ extern "C" int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, 
   float* hub = static_cast<float*>(hub_ws);
   const int nv = (C + 255) / 256;
   switch (nv) {
-    case 1: return launch_agg<1>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
-    case 2: return launch_agg<2>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
-    case 3: return launch_agg<3>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
-    default: return launch_agg<4>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, st);
+    case 1: return launch_agg<1>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
+    case 2: return launch_agg<2>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
+    case 3: return launch_agg<3>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
+    default: return launch_agg<4>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
   }
 }

@@ -166,17 +166,22 @@ def as_view(graph, num_nodes: int) -> GraphView:
 # raw kernel wrappers
 # ---------------------------------------------------------------------------
 def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False,
-                  hub_rows=None):
+                  hub_rows=None, row_range=None):
+    """row_range=(r0, r1): aggregate only destination rows [r0, r1) (x holds all rows) - the row-sharded encoder."""
     _need_cuda(x)
     assert x.dtype == BF16 and x.is_contiguous()
-    N, C = x.shape
+    total, C = x.shape
+    r0, r1 = row_range if row_range is not None else (0, total)
+    N = r1 - r0
     out = torch.empty(N, C, dtype=torch.float32 if out_fp32 else BF16, device=x.device)
+    if N == 0:
+        return out
     if drop_keep is not None:
         drop_keep = drop_keep.contiguous().view(torch.uint8) if drop_keep.dtype == torch.bool else drop_keep.contiguous()
     cap = int(colind.numel())
     # split-row partials for hub rows (power-law graphs); hub_rows=None means "the graph cannot have hub rows": no pre-pass
     ws = _ws(lib.bmkg_gcn_aggregate_workspace_bytes(cap, C), x.device) if hub_rows is not None else None
-    call("bmkg_gcn_aggregate", _p(rowptr), _p(colind), _p(dis), _p(x), N, C, _p(bias), int(relu), float(drop_p),
+    call("bmkg_gcn_aggregate_rows", _p(rowptr), _p(colind), _p(dis), _p(x), total, r0, N, C, _p(bias), int(relu), float(drop_p),
          int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep), _p(out), int(out_fp32), cap, _p(hub_rows), _p(ws),
          ws.numel() if ws is not None else 0, _stream())
     return out

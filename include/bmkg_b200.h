@@ -77,6 +77,13 @@ int bmkg_gcn_aggregate(const int32_t* rowptr, const int32_t* colind, const float
                        void* out, int out_is_fp32, int64_t nnz_capacity, const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes,
                        void* stream);
 
+/* Row-sharded variant: aggregates destination rows [row_begin, row_begin + num_rows) of the graph (rowptr/dis indexed by the
+ * global row, x_bf16 = all total_rows rows, e.g. all-gathered over NVLink) into a num_rows x C output. */
+int bmkg_gcn_aggregate_rows(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* x_bf16, int64_t total_rows,
+                            int64_t row_begin, int64_t num_rows, int channels, const float* bias, int relu, float drop_p,
+                            uint64_t drop_seed, const uint8_t* drop_keep, void* out, int out_is_fp32, int64_t nnz_capacity,
+                            const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes, void* stream);
+
 /* ---- A3/A4: GAT aggregation (extension - BASELINE.json configs 2 and 5) ---------------------------
  * PyG GATConv(in, out, heads=H, concat=True, negative_slope, add_self_loops=True) semantics;
  * no reference call site on the GCL path (nearest: RGAT, biomedkg/model/encoder.py:62-121).
