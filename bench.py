@@ -176,7 +176,7 @@ def run_ours(args, rank, world, local_rank):
         if full_shard:
             from biomedkg_b200.dist import allreduce_grads, sharded_grace_loss
 
-            loss = sharded_grace_loss(mod, batch.x, batch.edge_index)
+            loss = sharded_grace_loss(mod, batch.x, batch.edge_index, num_nodes=getattr(batch, "num_nodes", None))
             loss.backward()
             allreduce_grads(params)                 # per-rank partial sums -> full gradient
         else:
@@ -239,11 +239,19 @@ def run_ours(args, rank, world, local_rank):
     # runs every step) and reads the loss back.  The copy of step k+1 is issued on a side stream while step k computes
     # (pinned-memory prefetch, as a DataLoader with pin_memory does); all copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
+    x_src = x_host
+    if full_shard:   # a sharded loader moves only this rank's node block of the features (edge_index stays replicated)
+        from biomedkg_b200.dist import node_partition
+
+        b0, b1 = node_partition(N, world)[1][rank]
+        x_src = x_host[b0:b1].contiguous().pin_memory()
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
             bt = Batch()
-            bt.x = x_host.to(dev, non_blocking=True)
+            bt.x = x_src.to(dev, non_blocking=True)
+            if full_shard:
+                bt.num_nodes = N
             bt.edge_index = ei_host.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
@@ -274,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8,
+    e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": (x_src.numel() * 4 + ei_host.numel() * 8) * (world if rowshard else 1),
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
            "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"}
 

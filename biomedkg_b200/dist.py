@@ -227,22 +227,28 @@ def sharded_gcn_encoder(encoder, x_loc, view, r0, r1, num_nodes, block, group):
     return x
 
 
-def sharded_grace_loss(module, x, edge_index, group=None):
+def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
     """GRACEModule.training_step's loss with the node rows split over the ranks of ``group``.
 
     Every rank receives the same (x, edge_index) and the same parameters / RNG state.  Fusion, feature masks, the GCN layers'
     GEMMs, the projector and the normalisation run on this rank's node block only; each GCN layer all-gathers its transformed
     rows (bf16 [N,256] over NVLink) before aggregating its own destination rows; the projected views are all-gathered once and
     the InfoNCE is split by rows of Z (sharded_infonce_loss).  The loss is the single-GPU full-graph loss; parameter gradients
-    are partial sums that the caller all-reduces (``allreduce_grads``)."""
+    are partial sums that the caller all-reduces (``allreduce_grads``).
+
+    ``x`` is either the full feature tensor (every rank slices its rows) or, with ``num_nodes`` given, only this rank's block
+    ``node_partition(num_nodes, world)[1][rank]`` - a sharded loader then moves 1/world of the features per rank."""
     from . import ops
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     model = module.model
-    N = x.size(0)
+    N = int(num_nodes) if num_nodes is not None else x.size(0)
     block, parts = node_partition(N, world)
     r0, r1 = parts[rank]
-    fused = module.fusion_fn(x[r0:r1])                                   # row-local (attention fusion / mean)
+    x_loc = x if num_nodes is not None else x[r0:r1]
+    if x_loc.size(0) != r1 - r0:
+        raise ValueError("x must hold this rank's node block when num_nodes is given")
+    fused = module.fusion_fn(x_loc)                                      # row-local (attention fusion / mean)
     draws = model.draws
     m1 = draws.feature_mask(x.new_empty(N, fused.size(1)), 0.4)          # full-size draws in the reference's order, then sliced:
     m2 = draws.feature_mask(x.new_empty(N, fused.size(1)), 0.4)          # identical masks whatever the world size
