@@ -108,3 +108,33 @@ def test_sharded_infonce_matches_single_process_oracle(n, d, world):
         assert torch.allclose(g1.double(), h1.grad, rtol=1e-4, atol=1e-7)
         assert torch.allclose(g2.double(), h2.grad, rtol=1e-4, atol=1e-7)
     assert out[0][0] == out[1][0]                      # every rank ends with the same loss
+
+
+def _gather_worker(rank, world, port, n, c, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from biomedkg_b200.dist import _GatherRowsFn, node_partition
+
+        block, parts = node_partition(n, world)
+        r0, r1 = parts[rank]
+        full = torch.arange(n * c, dtype=torch.float32).view(n, c)
+        local = full[r0:r1].clone().requires_grad_(True)
+        gathered = _GatherRowsFn.apply(local, n, block, r0, None)
+        w = torch.arange(n, dtype=torch.float32).view(n, 1) + 1.0      # every rank applies the SAME function downstream
+        (gathered * w).sum().backward()
+        out[rank] = (torch.equal(gathered.detach(), full), torch.equal(local.grad, w[r0:r1].expand(-1, c)), (r0, r1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 1])
+def test_node_partition_and_row_gather(n):
+    from biomedkg_b200.dist import node_partition
+
+    block, parts = node_partition(n, 2)
+    assert parts[0][0] == 0 and parts[-1][1] == n and parts[0][1] == parts[1][0] and block * 2 >= n
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, _free_port(), n, 3, out), nprocs=2, join=True)
+    assert all(out[r][0] and out[r][1] for r in range(2)), dict(out)
