@@ -593,6 +593,13 @@ class _InfoNCEFn(torch.autograd.Function):
 def infonce_loss(h1, h2, tau=0.2):
     if h1.shape != h2.shape or h1.dim() != 2:
         raise ValueError("h1 and h2 must both be [N, D]")
+    D = h1.size(1)
+    if D > 256:
+        raise ValueError("the fused InfoNCE kernels hold one 128 x D row block on chip: D <= 256 (reference default 256)")
+    if D % 64:   # the tcgen05 K loop works on 64-column panels: zero columns change neither the norms nor the dot products
+        pad = 64 - D % 64
+        h1 = torch.nn.functional.pad(h1, (0, pad))
+        h2 = torch.nn.functional.pad(h2, (0, pad))
     return _InfoNCEFn.apply(h1, h2, float(tau))
 
 

@@ -9,7 +9,7 @@ from oracle import pygcl
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-CASES = [(5, 64), (64, 64), (128, 256), (200, 128), (1000, 256), (1025, 192), (4096, 256), (6000, 256)]
+CASES = [(5, 64), (64, 64), (128, 256), (200, 128), (1000, 256), (1025, 192), (4096, 256), (6000, 256), (300, 100), (257, 40)]
 
 
 @pytest.mark.parametrize("n,d", CASES)
