@@ -123,7 +123,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
       int stage = 0;
       uint32_t sphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int cc = item % sch.nchunks;
+        const int cc = item / sch.nrb;  // chunk-major: all CTAs sweep the same column chunk together (L2-resident)
         const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
         for (int ct = t0; ct < t1; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
@@ -141,7 +141,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
       int stage = 0, acc = 0;
       uint32_t sphase = 0, accphase = 0, aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int cc = item % sch.nchunks;
+        const int cc = item / sch.nrb;  // chunk-major: all CTAs sweep the same column chunk together (L2-resident)
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::tc_fence_after();
@@ -179,7 +179,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
     int tcount = 0;
     uint32_t aphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int rb = sch.rb0 + item / sch.nchunks, cc = item % sch.nchunks;
+      const int rb = sch.rb0 + item % sch.nrb, cc = item / sch.nrb;
       const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
       if (wg == 0) {  // stage this item's 128 stationary rows into TMEM once the previous item's MMAs retired
         ptx::mbar_wait(a_empty, aphase ^ 1);
@@ -818,6 +818,12 @@ static Schedule make_schedule(int64_t rows, int64_t row_begin, int64_t row_end) 
   s.nrb = (int)ceil_div(row_end - row_begin, kBM);
   s.ntiles = (int)ceil_div(rows, kBN);
   int chunks = (int)ceil_div(2 * kNumSMs, s.nrb);  // aim for >= 2 work items per SM
+  // L2 blocking: when Z (rows x 512 B at D = 256) is much larger than the 126 MB L2, sweep it in column chunks of <= 48 MB
+  // that every CTA works on at the same time (work items are ordered chunk-major), so column tiles are fetched from HBM once
+  // per chunk instead of once per row block.
+  const int64_t chunk_rows_l2 = (48ll << 20) / 512;
+  const int l2_chunks = (int)ceil_div(rows, chunk_rows_l2);
+  if (l2_chunks > 2 && l2_chunks > chunks) chunks = l2_chunks;
   if (chunks > s.ntiles) chunks = s.ntiles;
   if (chunks < 1) chunks = 1;
   s.tiles_per_chunk = (int)ceil_div(s.ntiles, chunks);
