@@ -9,8 +9,9 @@ Importing the package loads libbmkg_b200.so and fails loudly if it is missing.
 """
 from . import _cabi  # noqa: F401  (raises ImportError if the kernel library was not built)
 from . import ops  # noqa: F401
+from . import export  # noqa: F401
 from .factory import FusionFactory
 from .gcl_module import BaseGCL, DGIModule, GGDModule, GRACEModule
 from .model import DGI, GGD, GRACE, GCNConv, GCNEncoder
 
-__all__ = ["FusionFactory", "BaseGCL", "DGIModule", "GGDModule", "GRACEModule", "DGI", "GGD", "GRACE", "GCNConv", "GCNEncoder", "ops"]
+__all__ = ["FusionFactory", "BaseGCL", "DGIModule", "GGDModule", "GRACEModule", "DGI", "GGD", "GRACE", "GCNConv", "GCNEncoder", "ops", "export"]

@@ -47,6 +47,7 @@ SIGNATURES = {
     "bmkg_gcn_aggregate_workspace_bytes": (SZ, [I64, I]),
     "bmkg_gcn_aggregate": (I, [P, P, P, P, I64, I, P, I, F, U64, P, P, I, I64, P, P, SZ, P]),
     "bmkg_gcn_aggregate_rows": (I, [P, P, P, P, I64, I64, I64, I, P, I, F, U64, P, P, I, I64, P, P, SZ, P]),
+    "bmkg_gcn_star_aggregate": (I, [P, P, P, P, P, I64, I, P, I, P, I, P]),
     "bmkg_gat_scores": (I, [P, P, P, I64, I, I, P, P, P]),
     "bmkg_gat_workspace_bytes": (SZ, [I64, I, I]),
     "bmkg_gat_aggregate": (I, [P, P, P, P, P, I64, I, I, F, P, I, F, U64, P, P, I, P, P, I64, P, P, SZ, P]),
@@ -109,7 +110,7 @@ def bind_thread(device_index: int) -> None:
 #: pre-passes of the aggregation kernels are not counted - a lower bound)
 KERNELS_PER_CALL = {
     "bmkg_edge_sort": None,            # data dependent: 3 + 5 * passes + 2 (counted by formula in bench.py)
-    "bmkg_csr_filter": 6, "bmkg_gcn_aggregate": 1, "bmkg_gcn_aggregate_rows": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
+    "bmkg_csr_filter": 6, "bmkg_gcn_aggregate": 1, "bmkg_gcn_aggregate_rows": 1, "bmkg_gcn_star_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_l2norm_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,

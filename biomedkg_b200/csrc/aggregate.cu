@@ -32,17 +32,20 @@ struct AggEpilogue {
 };
 
 // acc[v][i] += sum_{k in [beg,end)} dis[colind[k]] * X[colind[k]][v*256 + lane*8 + i]   (CSR order, fp32)
-template <int NV>
+// STAR (1-hop export, see gcn_star_aggregate_kernel): neighbours are leaves of a star - weight 1, rows of X - and the row's
+// own self-loop entry takes weight dis[self_row] and its row from Xself instead.
+template <int NV, bool STAR = false>
 __device__ __forceinline__ void gather_accumulate(const int32_t* __restrict__ colind, const float* __restrict__ dis,
                                                   const __nv_bfloat16* __restrict__ X, int C, int beg, int end, int lane,
-                                                  const bool (&act)[NV], float (&acc)[NV][8]) {
+                                                  const bool (&act)[NV], float (&acc)[NV][8], int self_row = -1,
+                                                  const __nv_bfloat16* __restrict__ Xself = nullptr) {
   for (int base = beg; base < end; base += 32) {
     const int k = base + lane;
     int c = 0;
     float w = 0.f;
     if (k < end) {
       c = colind[k];
-      w = dis[c];
+      w = STAR ? (c == self_row ? dis[c] : 1.f) : dis[c];
     }
     const int cnt = min(32, end - base);
     for (int j = 0; j < cnt; j += kAggUnroll) {
@@ -54,7 +57,7 @@ __device__ __forceinline__ void gather_accumulate(const int32_t* __restrict__ co
         const int cj = __shfl_sync(0xffffffffu, c, src_lane);
         wj[t] = __shfl_sync(0xffffffffu, w, src_lane);
         if (j + t < cnt) {
-          const __nv_bfloat16* rp = X + (int64_t)cj * C + lane * 8;
+          const __nv_bfloat16* rp = ((STAR && cj == self_row) ? Xself : X) + (int64_t)cj * C + lane * 8;
 #pragma unroll
           for (int v = 0; v < NV; ++v)
             if (act[v]) u[t][v] = ldg_cached(rp + v * 256);
@@ -205,6 +208,67 @@ __global__ void __launch_bounds__(kAggWarps * 32) gcn_aggregate_kernel(const int
   }
 }
 
+// 1-hop "star" aggregation for the embedding-export path (biomedkg/data/node.py:193-241 drives BaseGCL.forward,
+// gcl_module.py:55-58, over NeighborLoader(num_neighbors=[-1]) batches of ONE seed, data_module.py:71-79).  In such a batch
+// the only edges are neighbour -> seed, so after gcn_norm every neighbour has degree 1 (its own self-loop) and the seed has
+// the same in-degree d as in the full graph.  All N star graphs therefore share one "leaf" chain per node and differ only in
+// the seed row:  out[s] = dis[s] * (sum_{j -> s, j != s} Tleaf[j] + dis[s] * Tseed[s]) + b,  dis = d^-1/2 - one pass over
+// the full-graph CSR per layer instead of N tiny forward passes.  Rows longer than kHubThreshold are simply walked by their
+// warp (export is a one-off pass).
+template <int NV, bool OUT_F32>
+__global__ void __launch_bounds__(kAggWarps * 32) gcn_star_aggregate_kernel(const int32_t* __restrict__ rowptr,
+                                                                            const int32_t* __restrict__ colind,
+                                                                            const float* __restrict__ dis,
+                                                                            const __nv_bfloat16* __restrict__ Xleaf,
+                                                                            const __nv_bfloat16* __restrict__ Xseed, int64_t N, int C,
+                                                                            const float* __restrict__ bias, int relu,
+                                                                            void* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+  if (row >= N) return;
+  float acc[NV][8];
+  bool act[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    act[v] = (v * 256 + lane * 8) < C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+  }
+  gather_accumulate<NV, true>(colind, dis, Xleaf, C, rowptr[row], rowptr[row + 1], lane, act, acc, (int)row, Xseed);
+  const float di = dis[row];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    if (!act[v]) continue;
+    const int c0 = v * 256 + lane * 8;
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r[i] = acc[v][i] * di + (bias ? bias[c0 + i] : 0.f);
+      if (relu) r[i] = fmaxf(r[i], 0.f);
+    }
+    if (OUT_F32) {
+      float* o = static_cast<float*>(out) + row * C + c0;
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    } else {
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + row * C + c0) = pack8(r);
+    }
+  }
+}
+
+template <int NV>
+static int launch_star(const int32_t* rowptr, const int32_t* colind, const float* dis, const __nv_bfloat16* xl,
+                       const __nv_bfloat16* xs, int64_t N, int C, const float* bias, int relu, void* out, int out_f32,
+                       cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div(N, kAggWarps);
+  if (out_f32)
+    gcn_star_aggregate_kernel<NV, true><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out);
+  else
+    gcn_star_aggregate_kernel<NV, false><<<grid, kAggWarps * 32, 0, st>>>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
 template <int NV>
 static int launch_agg(const int32_t* rowptr, const int32_t* colind, const float* dis, const __nv_bfloat16* X, int64_t N, int C,
                       const AggEpilogue& ep, void* out, int out_f32, float* hub_partial, const int32_t* hub_rows, int64_t nnz_capacity,
@@ -268,5 +332,23 @@ extern "C" int bmkg_gcn_aggregate_rows(const int32_t* rowptr, const int32_t* col
     case 2: return launch_agg<2>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
     case 3: return launch_agg<3>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
     default: return launch_agg<4>(rowptr, colind, dis, X, N, C, ep, out, out_is_fp32, hub, hub_rows, nnz_capacity, row_begin, total_rows, st);
+  }
+}
+
+
+extern "C" int bmkg_gcn_star_aggregate(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* leaf_bf16,
+                                       const void* seed_bf16, int64_t N, int C, const float* bias, int relu, void* out,
+                                       int out_is_fp32, void* stream) {
+  BMKG_REQUIRE(rowptr && colind && dis && leaf_bf16 && seed_bf16 && out, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(N > 0 && N < (1ll << 31) && C > 0 && C % 8 == 0 && C <= 1024, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(leaf_bf16) && aligned16(seed_bf16) && aligned16(out), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xl = static_cast<const __nv_bfloat16*>(leaf_bf16);
+  const __nv_bfloat16* xs = static_cast<const __nv_bfloat16*>(seed_bf16);
+  switch ((C + 255) / 256) {
+    case 1: return launch_star<1>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out, out_is_fp32, st);
+    case 2: return launch_star<2>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out, out_is_fp32, st);
+    case 3: return launch_star<3>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out, out_is_fp32, st);
+    default: return launch_star<4>(rowptr, colind, dis, xl, xs, N, C, bias, relu, out, out_is_fp32, st);
   }
 }

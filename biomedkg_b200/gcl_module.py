@@ -23,14 +23,51 @@ try:  # pragma: no cover - lightning is not installed in the build image
 except Exception:  # noqa: BLE001
 
     class LightningModule(torch.nn.Module):
+        """The slice of lightning.LightningModule the reference uses: hyper-parameter capture, ``log`` and the
+        checkpoint layout of ``Trainer.save_checkpoint`` / ``load_from_checkpoint`` (train_gcl.py:78-83, node.py:204-209):
+        ``{"state_dict": ..., "hyper_parameters": <kwargs of the outermost __init__>}``."""
+
         trainer = None
 
         def save_hyperparameters(self, *args, ignore=None, **kwargs):
-            self.hparams = getattr(self, "hparams", {})
+            import inspect
+
+            ignore = set([ignore] if isinstance(ignore, str) else (ignore or ()))
+            frame, outer = inspect.currentframe().f_back, None
+            while frame is not None and frame.f_code.co_name == "__init__" and frame.f_locals.get("self") is self:
+                outer, frame = frame, frame.f_back           # BaseGCL.__init__ <- GRACEModule.__init__ <- caller
+            hp = {}
+            if outer is not None:
+                info = inspect.getargvalues(outer)
+                for name in info.args[1:]:
+                    if name not in ignore:
+                        hp[name] = info.locals[name]
+                if info.keywords:
+                    hp.update({k: v for k, v in info.locals[info.keywords].items() if k not in ignore})
+            self.hparams = hp
 
         def log(self, name, value, **kwargs):
             self.logged = getattr(self, "logged", {})
             self.logged[name] = value.detach() if torch.is_tensor(value) else value
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+        def save_checkpoint(self, path):
+            torch.save({"state_dict": self.state_dict(), "hyper_parameters": dict(self.hparams)}, path)
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **overrides):
+            import inspect
+
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            accepted = inspect.signature(cls.__init__).parameters
+            hp = {k: v for k, v in dict(ckpt.get("hyper_parameters", {})).items() if k in accepted}
+            hp.update(overrides)
+            obj = cls(**hp)
+            obj.load_state_dict(ckpt["state_dict"], strict=strict)
+            return obj.to(map_location) if map_location is not None else obj
 
 
 def _cosine_with_warmup(optimizer, num_warmup_steps, num_training_steps):

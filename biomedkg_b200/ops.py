@@ -187,6 +187,18 @@ def gcn_aggregate(rowptr, colind, dis, x, bias=None, relu=False, drop_p=0.0, dro
     return out
 
 
+def gcn_star_aggregate(rowptr, colind, dis, leaf, seed, bias=None, relu=False, out_fp32=False):
+    """out[s] = dis[s] * (sum_{j->s, j!=s} leaf[j] + dis[s] * seed[s]) + bias: every one-seed 1-hop star graph of the export
+    path (biomedkg/data/node.py:224-236) in one pass over the full-graph CSR."""
+    _need_cuda(leaf)
+    assert leaf.dtype == BF16 and seed.dtype == BF16 and leaf.is_contiguous() and seed.is_contiguous() and leaf.shape == seed.shape
+    N, C = leaf.shape
+    out = torch.empty(N, C, dtype=torch.float32 if out_fp32 else BF16, device=leaf.device)
+    call("bmkg_gcn_star_aggregate", _p(rowptr), _p(colind), _p(dis), _p(leaf), _p(seed), N, C, _p(bias), int(relu), _p(out),
+         int(out_fp32), _stream())
+    return out
+
+
 def colsum(z: torch.Tensor, row_weight: torch.Tensor | None = None) -> torch.Tensor:
     _need_cuda(z)
     z = z.contiguous()

@@ -84,6 +84,15 @@ int bmkg_gcn_aggregate_rows(const int32_t* rowptr, const int32_t* colind, const 
                             uint64_t drop_seed, const uint8_t* drop_keep, void* out, int out_is_fp32, int64_t nnz_capacity,
                             const int32_t* hub_rows, void* hub_ws, size_t hub_ws_bytes, void* stream);
 
+/* 1-hop "star" aggregation for the embedding-export path: biomedkg/data/node.py:193-241 calls BaseGCL.forward
+ * (biomedkg/gcl_module.py:55-58) once per seed node over NeighborLoader(num_neighbors=[-1]) batches
+ * (biomedkg/data_module.py:71-79).  All N one-seed star graphs are evaluated in one pass over the full-graph CSR:
+ *   out[s] = dis[s] * (sum_{j->s, j!=s} leaf[j] + dis[s] * seed[s]) + bias   (optionally ReLU),   dis = indeg^-1/2,
+ * leaf/seed bf16 [N,C] = the layer's linear transform of the leaf chain and of the seed chain. */
+int bmkg_gcn_star_aggregate(const int32_t* rowptr, const int32_t* colind, const float* dis, const void* leaf_bf16,
+                            const void* seed_bf16, int64_t num_nodes, int channels, const float* bias, int relu, void* out,
+                            int out_is_fp32, void* stream);
+
 /* ---- A3/A4: GAT aggregation (extension - BASELINE.json configs 2 and 5) ---------------------------
  * PyG GATConv(in, out, heads=H, concat=True, negative_slope, add_self_loops=True) semantics;
  * no reference call site on the GCL path (nearest: RGAT, biomedkg/model/encoder.py:62-121).

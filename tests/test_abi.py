@@ -95,3 +95,30 @@ def test_hash_mask_host_mirror():
     m = hash_keep_mask(1234, 200_000, 0.2)
     assert abs(float(m.float().mean()) - 0.8) < 5e-3
     assert torch.equal(m, hash_keep_mask(1234, 200_000, 0.2)) and not torch.equal(m, hash_keep_mask(1235, 200_000, 0.2))
+
+
+@pytest.mark.parametrize("name", ["grace_none", "grace_attention", "dgi_none", "ggd_none_a", "ggd_redaf"])
+def test_lightning_checkpoint_layout_loads_reference_state_dict(libpath, golden_dir, name, tmp_path):
+    """train_gcl.py:78-83 / node.py:204-209: a checkpoint holds the reference module's state_dict under "state_dict" and
+    the kwargs of the outermost __init__ under "hyper_parameters"; load_from_checkpoint must rebuild the module from
+    them and load every key strictly (the state_dict here was produced by the reference's own module)."""
+    import torch
+
+    import biomedkg_b200 as b
+
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg = fx["cfg"]
+    hp = dict(in_dim=cfg["in_dim"], hidden_dim=cfg["hidden_dim"], out_dim=cfg["out_dim"], num_hidden_layers=cfg["num_hidden_layers"],
+              scheduler_type="cosine", learning_rate=2e-4, warm_up_ratio=0.03, fuse_method=cfg["fuse_method"])
+    path = str(tmp_path / "epoch=0.ckpt")
+    torch.save({"state_dict": {k: v.float() for k, v in fx["state_dict"].items()}, "hyper_parameters": hp,
+                "pytorch-lightning_version": "2.2.1", "epoch": 0}, path)
+    cls = getattr(b, cfg["cls"])
+    mod = cls.load_from_checkpoint(path)
+    assert set(mod.state_dict()) == set(fx["state_dict"])
+    for k, v in mod.state_dict().items():
+        assert torch.equal(v, fx["state_dict"][k].float()), k
+    # and our own save -> load round trip keeps the captured hyper-parameters
+    mod.save_checkpoint(path)
+    again = cls.load_from_checkpoint(path)
+    assert {k: again.hparams[k] for k in hp} == hp

@@ -163,3 +163,44 @@ def test_gat_conv_matches_dense_softmax():
         e = torch.nn.functional.leaky_relu((xh[src] * a_s.view(-1)).sum(-1) + (xh[i] * a_d.view(-1)).sum(), 0.2)
         ref[i] = torch.softmax(e, 0) @ xh[src]
     assert torch.allclose(out, ref + b, atol=1e-12)
+
+
+# ---- embedding-export path (node.py:193-241) ----------------------------------------------------
+def _export_case(seed=0, N=40, M=2, IN=32, fuse="attention"):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, M, IN, generator=g, dtype=torch.float64) if M else torch.randn(N, IN, generator=g, dtype=torch.float64)
+    ei = torch.randint(0, N - 3, (2, 200), generator=g)            # the last 3 nodes stay isolated
+    ei[:, :5] = torch.tensor([[1, 1, 2, 3, 4], [1, 1, 2, 0, 0]])    # existing (and duplicated) self-loops
+    ei = torch.cat([ei, ei[:, 10:20]], dim=1)                       # duplicate edges
+    torch.manual_seed(seed)
+    m = om.GRACEModule(in_dim=IN, hidden_dim=64, out_dim=64, num_hidden_layers=2, fuse_method=fuse).double().eval()
+    for layer in m.model.encoder.graph_layers:
+        layer.bias.data.normal_(generator=g)
+    return m, x, ei
+
+
+def test_one_hop_batch_is_a_star():
+    from oracle import export as oe
+
+    ei = torch.tensor([[5, 2, 5, 3, 3, 0], [3, 3, 3, 3, 1, 5]])
+    nodes, sub = oe.one_hop_batch(ei, 3)
+    assert nodes.tolist() == [3, 5, 2]                                # seed first, neighbours in order of first appearance
+    assert sub.tolist() == [[1, 2, 1, 0], [0, 0, 0, 0]]               # duplicates kept, the 3->3 loop kept, nothing else
+    nodes, sub = oe.one_hop_batch(ei, 4)
+    assert nodes.tolist() == [4] and sub.shape == (2, 0)
+
+
+@pytest.mark.parametrize("fuse,M", [("attention", 2), (None, 2), ("none", 0)])
+def test_export_loop_equals_two_chain_closed_form(fuse, M):
+    from oracle import export as oe
+
+    m, x, ei = _export_case(seed=3, M=M, fuse=fuse)
+    loop, closed = oe.export_loop(m, x, ei), oe.export_two_chains(m, x, ei)
+    assert loop.shape == (40, 64)
+    assert float((loop - closed).abs().max()) < 1e-12 * max(1.0, float(loop.abs().max()))
+    # an isolated node's star is the node alone: its embedding is the plain per-node MLP chain
+    h = m.fusion_fn(x=x)[-1:]
+    for i, layer in enumerate(m.model.encoder.graph_layers):
+        h = h @ layer.lin.weight.t() + layer.bias
+        h = torch.relu(h) if i < len(m.model.encoder.graph_layers) - 1 else h
+    assert torch.allclose(loop[-1:], h, atol=1e-12)
