@@ -68,6 +68,9 @@ SIGNATURES = {
     "bmkg_fusion_attn_fwd": (I, [P, P, I64, I, I, P, P, P]),
     "bmkg_fusion_attn_bwd": (I, [P, P, P, P, I64, I, I, P, P]),
     "bmkg_mask_cast_bwd": (I, [P, P, P, P, P, I64, P, P]),
+    "bmkg_redaf_partial_rows": (I64, [I64, I]),
+    "bmkg_redaf_fwd": (I, [P, P, P, I64, I, I, F, U64, P, P, P]),
+    "bmkg_redaf_bwd": (I, [P, P, P, P, I64, I, I, F, U64, P, P, P, P]),
     "bmkg_colsum_bf16": (I, [P, P, P, I64, I, I, P, P, P, SZ, P]),
     "bmkg_infonce_padded_rows": (I64, [I64]),
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
@@ -115,6 +118,7 @@ KERNELS_PER_CALL = {
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
     "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
+    "bmkg_redaf_fwd": 1, "bmkg_redaf_bwd": 1,
 }
 kernel_launches = 0
 

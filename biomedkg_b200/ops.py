@@ -560,6 +560,43 @@ def fusion_attention(qkv, bias, N, M, E):
     return _FusionAttnFn.apply(qkv, bias, N, M, E)
 
 
+class _RedafFn(torch.autograd.Function):
+    """ReDAF epilogue (utils/fusion.py:70-90): t = bias-free x W^T (bf16 [N,M,E]); Linear bias and the gate are applied in
+    the kernel together with both ReLUs, dropout and the modality mean."""
+
+    @staticmethod
+    def forward(ctx, t, bias, gate, drop_p, drop_seed, drop_keep):
+        _need_cuda(t)
+        assert t.dtype == BF16 and t.is_contiguous() and t.dim() == 3
+        N, M, E = t.shape
+        b, g = bias.detach().float().contiguous(), gate.detach().float().contiguous()
+        if drop_keep is not None:
+            drop_keep = drop_keep.contiguous().view(torch.uint8) if drop_keep.dtype == torch.bool else drop_keep.contiguous()
+        out = torch.empty(N, E, dtype=torch.float32, device=t.device)
+        call("bmkg_redaf_fwd", _p(t), _p(b), _p(g), N, M, E, float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _p(drop_keep),
+             _p(out), _stream())
+        ctx.save_for_backward(t, b, g, drop_keep)
+        ctx.drop = (float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        t, b, g, keep = ctx.saved_tensors
+        N, M, E = t.shape
+        gout = gout.contiguous().float()
+        dt = torch.empty_like(t)
+        rows = int(lib.bmkg_redaf_partial_rows(N, E))
+        part = torch.empty(rows, M * E, dtype=torch.float32, device=t.device)
+        call("bmkg_redaf_bwd", _p(t), _p(b), _p(g), _p(gout), N, M, E, ctx.drop[0], ctx.drop[1], _p(keep), _p(dt), _p(part), _stream())
+        dgate = _colsum_any(part).view(M, E) if ctx.needs_input_grad[2] else None
+        db = colsum_bf16(dt.view(N * M, E))[0] if ctx.needs_input_grad[1] else None
+        return dt, db, dgate, None, None, None
+
+
+def redaf_fuse(t, bias, gate, drop_p=0.0, drop_seed=0, drop_keep=None):
+    return _RedafFn.apply(t, bias, gate, drop_p, drop_seed, drop_keep)
+
+
 # ---------------------------------------------------------------------------
 # fused InfoNCE
 # ---------------------------------------------------------------------------

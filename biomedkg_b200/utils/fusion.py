@@ -29,7 +29,8 @@ class AttentionFusion(nn.Module):
 
 
 class ReDAF(nn.Module):
-    """utils/fusion.py:34-90 (sub_type_ids=None, relational_context=0.2 as every caller uses it)."""
+    """utils/fusion.py:34-90 (sub_type_ids=None, relational_context=0.2 as every caller uses it): the transform is one
+    bf16 GEMM, everything after it (bias, ReLU, gate, dropout, ReLU, mean over modalities) one fused kernel."""
 
     def __init__(self, embed_dim: int, num_modalities: int = 2):
         super().__init__()
@@ -45,11 +46,15 @@ class ReDAF(nn.Module):
     def forward(self, x, relational_context=0.2, sub_type_ids=None):
         if sub_type_ids is not None:
             raise NotImplementedError("sub_type_ids is never passed on the GCL path")
+        if x.dim() != 3 or x.size(1) != self.num_modalities:
+            raise ValueError(f"ReDAF expects [N, {self.num_modalities}, E] stacked modality embeddings")  # fusion.py:58-60,75-79 broadcast
+        N, M, E = x.shape
         ctx = torch.full((1, self.embed_dim), relational_context, device=x.device, dtype=torch.float32)
         zeta = torch.sigmoid(torch.nn.functional.linear(ctx, self.relational_context_layer.weight, self.relational_context_layer.bias))
-        t = self.activation(ops.linear(x, self.transform_layer.weight, self.transform_layer.bias))
-        gate = self.modal_weights.transpose(0, 1) * zeta.unsqueeze(0)            # [1, M, E]
-        h = self.activation(self.dropout(t * gate))
-        if h.dim() == 3:
-            h = ops.modality_mean(h)
-        return h
+        gate = self.modal_weights.squeeze(1) * zeta                               # [M, E] (fusion.py:82-84)
+        t = ops.linear(x.reshape(N * M, E), self.transform_layer.weight, None, out_bf16=True).view(N, M, E)
+        p, seed, keep = 0.0, 0, None
+        if self.training:
+            p = self.dropout.p
+            seed, keep = self.draws.dropout((N, M, E), p, x.device)
+        return ops.redaf_fuse(t.contiguous(), self.transform_layer.bias, gate, p, seed, keep)

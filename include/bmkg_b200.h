@@ -166,6 +166,20 @@ int bmkg_fusion_attn_fwd(const void* qkv_bf16, const float* qkv_bias, int64_t nu
 int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* qkv_bias, const float* probs, const float* dout, int64_t num_nodes,
                          int modalities, int embed, void* dqkv_bf16, void* stream);
 
+/* ---- F2: ReDAF fusion epilogue -------------------------------------------------------------
+ * biomedkg/utils/fusion.py:70-90 after the transform GEMM: out[n] = mean_m relu(dropout_p(relu(t[n,m] + bias) * gate[m])),
+ * gate[m] = modal_weights[m] * sigmoid(relational_context_layer(0.2 * 1)) (fusion.py:54-56,82-84) computed by the caller.
+ * t bf16 [N,M,E] = bias-free x W^T; bias fp32 [E]; gate fp32 [M,E]; out fp32 [N,E]; M <= 4, E % 8 == 0.
+ * Dropout: drop_keep uint8 [N,M,E] if given, else the counter hash on (drop_seed, flat index), else none (drop_p = 0).
+ * Backward: dt bf16 [N,M,E] (gradient w.r.t. t, hence also w.r.t. t + bias) and per-CTA partial sums
+ * dgate_partial fp32 [bmkg_redaf_partial_rows(N,E), M, E] whose column sums (bmkg_colsum) are d gate. */
+int64_t bmkg_redaf_partial_rows(int64_t num_nodes, int embed);
+int bmkg_redaf_fwd(const void* t_bf16, const float* bias, const float* gate, int64_t num_nodes, int modalities, int embed,
+                   float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, float* out, void* stream);
+int bmkg_redaf_bwd(const void* t_bf16, const float* bias, const float* gate, const float* dout, int64_t num_nodes, int modalities,
+                   int embed, float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, void* dt_bf16, float* dgate_partial,
+                   void* stream);
+
 /* ---- I1/I2: fused GRACE InfoNCE (tcgen05 / TMEM / TMA) -----------------------------------
  * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).
  * z bf16 [2N, D]: rows [0,N) = normalize(h1) * sqrt(log2e/tau), rows [N,2N) = same for h2

@@ -235,3 +235,87 @@ def test_gcn_aggregate_cfg4_size_vs_torch_sparse():
     out_y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, y, out_fp32=True)
     out_xy = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, (x.float() + y.float()).bfloat16(), out_fp32=True)
     assert rel_err(out_xy, out + out_y) < 5e-3            # linearity up to the bf16 rounding of x + y
+
+
+# ---- F2: ReDAF fused epilogue (utils/fusion.py:34-90) ------------------------------------------------------------
+def _redaf_pair(E, seed):
+    from biomedkg_b200.utils.fusion import ReDAF
+    from oracle import models as om
+
+    torch.manual_seed(seed)
+    orc = om.ReDAF(E).double()
+    with torch.no_grad():
+        orc.modal_weights.normal_(1.0, 0.5)            # some gates negative: the second ReLU must cut them
+        orc.transform_layer.bias.normal_(0.0, 0.2)
+    red = ReDAF(E)
+    red.load_state_dict({k: v.float() for k, v in orc.state_dict().items()})
+    return orc, red.to(DEV)
+
+
+@pytest.mark.parametrize("N,E", [(257, 64), (1000, 768), (33, 40)])
+def test_redaf_training_step_replayed_draws(N, E):
+    """Forward + every gradient of ReDAF in training mode, the oracle's recorded dropout mask replayed on the device."""
+    from biomedkg_b200.draws import ReplayDraws
+    from oracle import models as om
+
+    orc, red = _redaf_pair(E, 3)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(N, 2, E, generator=g)
+    x = x / x.norm(dim=1, keepdim=True)
+    x = x.to(torch.bfloat16).float()                   # representable inputs: differences come from the GEMM rounding only
+    w = torch.randn(N, E, generator=g).double()
+    orc.train()
+    orc.draws = om.TorchDraws()
+    xr = x.double().requires_grad_(True)
+    out_ref = orc(xr)
+    (out_ref * w).sum().backward()
+    red.train()
+    red.draws = ReplayDraws(orc.draws.log, DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = red(xd)
+    (out * w.float().to(DEV)).sum().backward()
+    assert out.dtype == torch.float32 and out.shape == (N, E)
+    assert rel_err(out, out_ref) < 1e-2
+    # The bf16 pre-activation flips the first ReLU's decision for the ~0.1 % of elements with |Wx + b| below its rounding
+    # error; each flip is a full-size error in dt, so the Frobenius error goes like sqrt(fraction flipped) ~ 3 % while the
+    # direction is unaffected (same effect and bound as the encoder's ReLUs, DESIGN.md "Parity").
+    assert rel_err(xd.grad, xr.grad) < 6e-2
+    cos = torch.nn.functional.cosine_similarity(xd.grad.flatten().double().cpu(), xr.grad.flatten(), dim=0)
+    assert float(cos) > 0.999
+    refp = dict(orc.named_parameters())
+    for k, p in red.named_parameters():
+        if k.startswith("sub_type_embeddings"):
+            assert p.grad is None and refp[k].grad is None   # never used when sub_type_ids is None (fusion.py:62-68)
+            continue
+        assert rel_err(p.grad, refp[k].grad) < 6e-2, k
+
+
+def test_redaf_hashed_dropout_matches_host_mirror_and_eval_is_deterministic():
+    from biomedkg_b200 import ops
+    from biomedkg_b200.draws import hash_keep_mask
+
+    N, M, E = 300, 3, 128
+    g = torch.Generator().manual_seed(8)
+    t = torch.randn(N, M, E, generator=g).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(E, generator=g).to(DEV) * 0.1
+    gate = (torch.randn(M, E, generator=g) * 0.5 + 0.7).to(DEV)
+    seed, p = 0x1234ABCD5678, 0.1
+    keep = hash_keep_mask(seed, N * M * E, p).view(N, M, E).to(DEV)
+    assert 0.85 < float(keep.float().mean()) < 0.95
+    a = ops.redaf_fuse(t, bias, gate, p, seed, None)
+    b = ops.redaf_fuse(t, bias, gate, p, 0, keep)
+    assert torch.equal(a, b)
+    ref = torch.relu(torch.relu(t.double() + bias.double()) * gate.double() * keep.double() / (1 - p)).mean(dim=1)
+    assert rel_err(a, ref) < 1e-6
+    e1, e2 = ops.redaf_fuse(t, bias, gate), ops.redaf_fuse(t, bias, gate)
+    assert torch.equal(e1, e2)
+    assert rel_err(e1, torch.relu(torch.relu(t.double() + bias.double()) * gate.double()).mean(dim=1)) < 1e-6
+    # backward with the hashed stream equals backward with the explicit mask, bit for bit
+    outs = []
+    for kw in ((p, seed, None), (p, 0, keep)):
+        tt, bb, gg = t.clone().float().requires_grad_(True), bias.clone().requires_grad_(True), gate.clone().requires_grad_(True)
+        o = ops.redaf_fuse(tt.to(torch.bfloat16), bb, gg, *kw)
+        o.square().sum().backward()
+        outs.append((tt.grad, bb.grad, gg.grad))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
