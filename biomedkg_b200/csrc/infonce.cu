@@ -13,14 +13,14 @@
 //      loss = (1/2N) [ sum_u ln R_u - 2 ln2 sum_i z_i . z_{N+i} ].
 // |logit| <= 1/tau so a fixed shift replaces the online max: no rescale pass.
 //
-// Forward: persistent CTAs; each owns a 128-row block of Z (A operand, resident
-// in smem) and streams 128-row column tiles of Z (B operand) through a TMA +
-// mbarrier ring; tcgen05.mma (M=128,N=128,K=16, bf16 -> fp32) writes S tiles into
-// a 4-deep ring of TMEM accumulators; two softmax warpgroups pull tiles with
-// tcgen05.ld, apply ex2, mask the diagonal and keep per-row partial sums in
-// registers.  Backward: same stream; P = 2^S (1/R_u + 1/R_v) is written back to
-// TMEM as bf16 (aliasing S) and a second tcgen05.mma with A from TMEM and the
-// same smem tile as an MN-major B accumulates dZ_u = sum_v P_uv z_v in TMEM.
+// Forward: persistent CTAs; each work item is a 128-row block of Z (A operand, staged once into TMEM - the TS form
+// keeps it off the shared-memory read path) against a chunk of 128-row column tiles of Z (B operand) streamed through a
+// 3-stage TMA + mbarrier ring; tcgen05.mma (M=128,N=128,K=16, bf16 -> fp32) writes S tiles into a 3-deep ring of TMEM
+// accumulators; two softmax warpgroups pull tiles with tcgen05.ld, apply ex2, mask the diagonal and keep per-row
+// partial sums in registers.  Work items are ordered chunk-major, and when Z is larger than L2 the chunks are sized to
+// fit it, so all CTAs sweep the same L2-resident column chunk at the same time.  Backward: same stream;
+// P = 2^S (1/R_u + 1/R_v) is written back to TMEM as bf16 (aliasing S) and a second tcgen05.mma with A from TMEM and
+// the same smem tile as an MN-major B accumulates dZ_u = sum_v P_uv z_v in TMEM.
 //
 // Tensor-bound.  Algorithmic FLOPs: fwd 6 N^2 D, bwd 8 N^2 D.
 #include <cuda.h>
