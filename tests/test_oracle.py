@@ -204,3 +204,45 @@ def test_export_loop_equals_two_chain_closed_form(fuse, M):
         h = h @ layer.lin.weight.t() + layer.bias
         h = torch.relu(h) if i < len(m.model.encoder.graph_layers) - 1 else h
     assert torch.allclose(loop[-1:], h, atol=1e-12)
+
+
+# ---- hypothesis-driven properties -----------------------------------------------------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 40), st.lists(st.tuples(st.integers(0, 39), st.integers(0, 39)), min_size=0, max_size=120), st.randoms())
+def test_csr_properties_any_graph(n, edges, rnd):
+    """Any edge multiset (empty, ragged, duplicates, self-loops): the canonical CSR of the gcn_norm'ed view is invariant to
+    the order the edges arrive in, has exactly one self-loop per row, and its degree vector is what gcn_norm counts."""
+    edges = [(s % n, d % n) for s, d in edges]
+    ei = torch.tensor(edges, dtype=torch.int64).reshape(-1, 2).t().contiguous()
+    view = pyg.view_graph(ei, n)
+    rp, ci, _ = pyg.canonical_csr(view, n)
+    shuffled = list(edges)
+    rnd.shuffle(shuffled)
+    ei2 = torch.tensor(shuffled, dtype=torch.int64).reshape(-1, 2).t().contiguous()
+    rp2, ci2, _ = pyg.canonical_csr(pyg.view_graph(ei2, n), n)
+    assert torch.equal(rp, rp2) and torch.equal(ci, ci2)
+    non_self = sum(1 for s, d in edges if s != d)
+    assert int(rp[-1]) == non_self + n
+    for r in range(n):
+        row = ci[int(rp[r]) : int(rp[r + 1])].tolist()
+        assert row == sorted(row) and row.count(r) == 1
+        assert len(row) == 1 + sum(1 for s, d in edges if d == r and s != r)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(2, 24), st.integers(1, 12), st.integers(0, 2**31 - 1))
+def test_infonce_properties_any_shape(n, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    h1 = torch.randn(n, d, generator=g, dtype=torch.float64)
+    h2 = torch.randn(n, d, generator=g, dtype=torch.float64)
+    a = pygcl.infonce_l2l_as_written(h1, h2, 0.2, True)
+    assert abs(float(a - pygcl.infonce_l2l_closed_form(h1, h2, 0.2))) < 1e-10
+    scale = torch.rand(n, 1, generator=g, dtype=torch.float64) + 0.05
+    assert abs(float(a - pygcl.infonce_l2l_closed_form(h1 * scale, h2 / scale, 0.2))) < 1e-10     # row-scale invariant
+    assert abs(float(a - pygcl.infonce_l2l_closed_form(h2, h1, 0.2))) < 1e-10                     # symmetric in the views
+    p = torch.randperm(n, generator=g)
+    assert abs(float(a - pygcl.infonce_l2l_closed_form(h1[p], h2[p], 0.2))) < 1e-10               # node order does not matter
