@@ -111,3 +111,45 @@ def test_row_sharded_entry_points_compose(n, d, splits):
     assert torch.allclose(dz, full_dz, rtol=1e-4, atol=1e-9)
     ref = ops.infonce_loss(h1, h2, 0.2)
     assert abs(float(ref) - float(full_loss)) < 1e-6 * abs(float(ref))
+
+
+@pytest.mark.parametrize("n", [200_001, 9_000])
+def test_infonce_cluster_closed_form_large_n(n):
+    """Exact closed form at sizes no dense reference reaches (n = 200 001: Z is 205 MB > L2, so the forward runs its
+    L2-blocked chunk-major schedule with 5 column chunks; ragged last row block).  Every node is a one-hot cluster
+    direction (same in both views, random unbalanced assignment): S_uv = [c(u) = c(v)] / tau exactly in bf16, so with
+    n_c rows of Z per cluster  R_c = (n_c - 1) e^(1/tau) + (2N - n_c),  loss = mean_u ln R_c(u) - 1/tau  and
+    d loss / d h_u = sum_{c' != c(u)} n_c' (1/R_c(u) + 1/R_c') / (2 N tau) e_c'.  A skipped, repeated or mis-addressed
+    tile changes R or the gradient of the rows it touches."""
+    import math
+
+    from biomedkg_b200 import ops
+
+    K, d, tau = 64, 256, 0.2
+    g = torch.Generator().manual_seed(n)
+    c = (torch.rand(n, generator=g) ** 2 * K).long().clamp_(max=K - 1)        # unbalanced cluster sizes
+    h = torch.zeros(n, d)
+    h[torch.arange(n), c] = 1.0
+    h1, h2 = h.to(DEV).requires_grad_(True), h.clone().to(DEV).requires_grad_(True)
+    loss = ops.infonce_loss(h1, h2, tau)
+    loss.backward()
+    nc = 2.0 * torch.bincount(c, minlength=K).double()
+    # the kernel's operand is bf16(h/|h| * sqrt(log2e/tau)): for exactly-unit one-hot rows the rounding of that one scale
+    # factor is systematic (2.6858 -> 2.6875), i.e. the device evaluates the same formula at 1/tau_eff = s_bf16^2 * ln2
+    s_bf16 = float(torch.tensor(math.sqrt(math.log2(math.e) / tau)).to(torch.bfloat16))
+    inv_tau = s_bf16 * s_bf16 * math.log(2.0)
+    assert abs(inv_tau * tau - 1.0) < 2e-3                                     # inside the 1e-3-relative loss budget
+    R = (nc - 1.0) * math.exp(inv_tau) + (2.0 * n - nc)
+    ref = float((torch.log(R) * nc).sum() / (2.0 * n) - inv_tau)
+    assert abs(float(loss) - ref) <= 2e-5 * abs(ref), (float(loss), ref)
+    R = (nc - 1.0) * math.exp(1.0 / tau) + (2.0 * n - nc)                      # exact-arithmetic value: the stated tolerance
+    exact = float((torch.log(R) * nc).sum() / (2.0 * n) - 1.0 / tau)
+    assert abs(float(loss) - exact) <= 1e-3 * abs(exact)
+    G = nc[None, :] * (1.0 / R[:, None] + 1.0 / R[None, :]) / (2.0 * n * tau)
+    G.fill_diagonal_(0.0)
+    gref = torch.zeros(n, d, dtype=torch.float64)
+    gref[:, :K] = G[c]
+    for got in (h1.grad, h2.grad):
+        assert rel_err(got, gref) < 1e-2
+        row_err = (got.double().cpu() - gref).norm(dim=1) / gref.norm(dim=1)
+        assert float(row_err.max()) < 2e-2                                     # every row, not just on average
