@@ -68,6 +68,11 @@ SIGNATURES = {
     "bmkg_fusion_attn_fwd": (I, [P, P, I64, I, I, P, P, P]),
     "bmkg_fusion_attn_bwd": (I, [P, P, P, P, I64, I, I, P, P]),
     "bmkg_mask_cast_bwd": (I, [P, P, P, P, P, I64, P, P]),
+    "bmkg_sample_workspace_bytes": (SZ, [I64]),
+    "bmkg_sample_count": (I, [P, P, I64, I, P, P, SZ, P]),
+    "bmkg_sample_pick": (I, [P, P, P, P, I64, I, P, U64, I, I64, P, P, P, P]),
+    "bmkg_sample_relabel": (I, [P, I64, I64, P, P, P, P, P, P, SZ, P]),
+    "bmkg_sample_set_ids": (I, [P, I64, P, I, P]),
     "bmkg_redaf_partial_rows": (I64, [I64, I]),
     "bmkg_redaf_fwd": (I, [P, P, P, I64, I, I, F, U64, P, P, P]),
     "bmkg_redaf_bwd": (I, [P, P, P, P, I64, I, I, F, U64, P, P, P, P]),
@@ -118,7 +123,8 @@ KERNELS_PER_CALL = {
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
     "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
-    "bmkg_redaf_fwd": 1, "bmkg_redaf_bwd": 1,
+    "bmkg_redaf_fwd": 1, "bmkg_redaf_bwd": 1, "bmkg_sample_count": 3, "bmkg_sample_pick": 1, "bmkg_sample_relabel": 6,
+    "bmkg_sample_set_ids": 1,
 }
 kernel_launches = 0
 

@@ -93,6 +93,31 @@ int bmkg_gcn_star_aggregate(const int32_t* rowptr, const int32_t* colind, const 
                             const void* seed_bf16, int64_t num_nodes, int channels, const float* bias, int relu, void* out,
                             int out_is_fp32, void* stream);
 
+/* ---- S1: neighbour sampling (mini-batch regime) --------------------------------------------------
+ * torch_geometric NeighborLoader as configured at biomedkg/data_module.py:71-79 (num_neighbors=[-1]) and :81-99
+ * ([30]*3, batch_size seeds): per hop every node added in the previous hop draws min(in-degree, fanout) in-edges without
+ * replacement; sampled edges are the batch's only edges; new sources are appended in order of first appearance.
+ * Graph = raw CSR by destination of bmkg_edge_sort(by_src=0): rowptr_raw [N+1], colind = minor_sorted [E] (sources),
+ * eperm = perm_sorted [E] (original edge ids).  One hop = count -> pick -> relabel; fanout in [1,32] or -1 (all).
+ *   bmkg_sample_count:   off int32 [F+1] = exclusive prefix of min(deg, fanout) over the frontier; off[F] = T
+ *   bmkg_sample_pick:    out_src int32 [T] global source ids, out_col int64 [T] = frontier_base + frontier index (the
+ *                        target's batch-local id), out_eid int64 [T] original edge ids (or NULL); counter-based draws
+ *                        keyed by (seed, hop, node): deterministic and independent of the batch composition
+ *   bmkg_sample_relabel: local_id int32 [N] (-1 = not in the batch; seeds preset by bmkg_sample_set_ids) and first_pos
+ *                        int32 [N] (all INT32_MAX) persist across hops; new_nodes int32 [<=T] receives the newly reached
+ *                        nodes in order of first appearance (local ids n_before, n_before+1, ...), *new_count their number,
+ *                        out_row int64 [T] the batch-local source ids
+ *   bmkg_sample_set_ids: reset = 0: local_id[nodes[i]] = i (seeds);  reset = 1: local_id[nodes[i]] = -1 (end of batch) */
+size_t bmkg_sample_workspace_bytes(int64_t max_entries);
+int bmkg_sample_count(const int32_t* rowptr, const int32_t* frontier, int64_t frontier_len, int fanout, int32_t* off, void* ws,
+                      size_t ws_bytes, void* stream);
+int bmkg_sample_pick(const int32_t* rowptr, const int32_t* colind, const int32_t* eperm, const int32_t* frontier,
+                     int64_t frontier_len, int fanout, const int32_t* off, uint64_t seed, int hop, int64_t frontier_base,
+                     int32_t* out_src, int64_t* out_col, int64_t* out_eid, void* stream);
+int bmkg_sample_relabel(const int32_t* src, int64_t num_entries, int64_t n_before, int32_t* local_id, int32_t* first_pos,
+                        int32_t* new_nodes, int32_t* new_count, int64_t* out_row, void* ws, size_t ws_bytes, void* stream);
+int bmkg_sample_set_ids(const int32_t* nodes, int64_t n, int32_t* local_id, int reset, void* stream);
+
 /* ---- A3/A4: GAT aggregation (extension - BASELINE.json configs 2 and 5) ---------------------------
  * PyG GATConv(in, out, heads=H, concat=True, negative_slope, add_self_loops=True) semantics;
  * no reference call site on the GCL path (nearest: RGAT, biomedkg/model/encoder.py:62-121).

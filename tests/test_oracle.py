@@ -246,3 +246,49 @@ def test_infonce_properties_any_shape(n, d, seed):
     assert abs(float(a - pygcl.infonce_l2l_closed_form(h2, h1, 0.2))) < 1e-10                     # symmetric in the views
     p = torch.randperm(n, generator=g)
     assert abs(float(a - pygcl.infonce_l2l_closed_form(h1[p], h2[p], 0.2))) < 1e-10               # node order does not matter
+
+
+# ---- neighbour sampler (data_module.py:71-99) ---------------------------------------------------------
+def test_sampler_oracle_structure_and_uniformity():
+    from collections import Counter
+
+    from oracle import sampler as osamp
+
+    rng = np.random.default_rng(1)
+    n, e = 60, 900
+    ei = rng.integers(0, n - 4, (2, e))                 # nodes n-4.. are isolated
+    ei[:, :3] = [[5, 5, 9], [5, 5, 9]]                   # self-loops are ordinary edges for the sampler
+    seeds = [3, 57, 11, 20]
+    n_id, sub, eid = osamp.sample(ei, n, seeds, [5, 3, -1], 99)
+    assert n_id[: len(seeds)].tolist() == seeds and len(set(n_id.tolist())) == len(n_id)
+    assert (ei[0][eid] == n_id[sub[0]]).all() and (ei[1][eid] == n_id[sub[1]]).all()      # every edge is a real in-edge
+    assert len(set(eid.tolist())) == len(eid)                                              # without replacement
+    indeg = np.bincount(ei[1], minlength=n)
+    per_target = Counter(sub[1].tolist())
+    fan = {0: 5, 1: 3, 2: -1}
+    # hop of a local node = the hop in which it was appended; every node of hop < 3 samples min(deg, fanout) in-edges
+    first_seen, bounds, hop_of = {}, [len(seeds)], {}
+    for pos, (r, c) in enumerate(zip(sub[0].tolist(), sub[1].tolist())):
+        first_seen.setdefault(r, pos)
+    for i in range(len(n_id)):
+        hop_of[i] = 0 if i < len(seeds) else None
+    order = sorted((p, r) for r, p in first_seen.items() if r >= len(seeds))
+    assert [r for _, r in order] == list(range(len(seeds), len(n_id)))                    # appended in order of first appearance
+    for i, v in enumerate(n_id.tolist()):
+        if i in per_target:
+            assert per_target[i] <= indeg[v]
+    for i, v in enumerate(seeds):
+        assert per_target.get(i, 0) == min(indeg[v], 5)
+    assert per_target.get(1, 0) == 0 and indeg[57] == 0                                    # isolated seed stays alone
+    # each in-edge position equally likely, in both the "take" (deg > 2k) and the "leave out" (deg <= 2k) regimes
+    for deg, k in ((100, 30), (40, 30), (31, 30), (64, 32)):
+        cnt = Counter()
+        trials = 3000
+        for node in range(trials):
+            pos = osamp.pick_positions(5, 1, node, deg, k)
+            assert len(pos) == k and len(set(pos)) == k and pos == sorted(pos) and 0 <= pos[0] and pos[-1] < deg
+            cnt.update(pos)
+        exp = trials * k / deg
+        chi2 = sum((cnt[p] - exp) ** 2 / exp for p in range(deg)) / (1 - k / deg)
+        assert chi2 < deg + 6 * math.sqrt(2 * deg), (deg, k, chi2)
+    assert osamp.pick_positions(5, 0, 7, 12, 30) == list(range(12)) and osamp.pick_positions(5, 0, 7, 12, -1) == list(range(12))
