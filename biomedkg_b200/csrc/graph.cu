@@ -73,61 +73,95 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint64_
   tile_hist[(int64_t)threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
+// One pass of the stable scatter.  Keys are first ranked inside the tile (per-warp match_any ranking, warps and 32-key
+// groups in input order => stable) and staged in shared memory in (digit, input order); the write-out then walks the staged
+// tile linearly, so consecutive threads write consecutive global addresses inside each digit's run (16 keys = 128 B on
+// average) instead of one 8-byte sector write per key.
+constexpr size_t kRadixScatterSmem = (size_t)kRadixTile * (sizeof(uint64_t) + sizeof(uint32_t));
+
+__global__ void __launch_bounds__(kRadixThreads, 3) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
                                                                       const uint32_t* __restrict__ idx_in,
                                                                       uint64_t* __restrict__ keys_out,
                                                                       uint32_t* __restrict__ idx_out, int64_t n, int shift,
                                                                       const int* __restrict__ tile_off, int num_tiles) {
-  // cnt[w][d]: running output cursor of digit d for warp w; bin 256 collects out-of-range lanes
+  // cnt[w][d]: tile-local output cursor of digit d for warp w; bin 256 collects out-of-range lanes
   __shared__ int cnt[kRadixThreads / 32][kRadixBins + 1];
+  __shared__ int gofs[kRadixBins];   // global position of staged slot i with digit d = gofs[d] + i
+  __shared__ int sw[33];
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  uint64_t* skey = reinterpret_cast<uint64_t*>(stage_raw);
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(stage_raw + (size_t)kRadixTile * sizeof(uint64_t));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (kRadixThreads / 32) * (kRadixBins + 1); i += kRadixThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
 
   // each warp owns 512 consecutive keys and walks them 32 at a time, so ranks follow input order
-  const int64_t wbase = (int64_t)blockIdx.x * kRadixTile + (int64_t)warp * (kRadixItems * 32);
+  const int64_t tbase = (int64_t)blockIdx.x * kRadixTile;
+  const int64_t wbase = tbase + (int64_t)warp * (kRadixItems * 32);
   uint64_t k[kRadixItems];
-  uint32_t id[kRadixItems];
-  int d[kRadixItems];
+  int info[kRadixItems];  // digit (9 bits) | rank among the warp's equal digits << 9 | group size << 15 | leader << 22
+  const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int it = 0; it < kRadixItems; ++it) {
     int64_t i = wbase + it * 32 + lane;
     bool valid = i < n;
     k[it] = valid ? keys_in[i] : 0;
-    id[it] = valid ? idx_in[i] : 0;
-    d[it] = valid ? (int)((k[it] >> shift) & 255) : kRadixBins;
+    info[it] = valid ? (int)((k[it] >> shift) & 255) : kRadixBins;
   }
 #pragma unroll
   for (int it = 0; it < kRadixItems; ++it) {
-    unsigned m = __match_any_sync(0xffffffffu, d[it]);
-    if (lane == __ffs(m) - 1) cnt[warp][d[it]] += __popc(m);
+    // lanes holding the same digit, from 9 ballots (match.any is far slower than the vote path)
+    const int dg = info[it];
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+      const bool bit = (dg >> b) & 1;
+      const unsigned vote = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? vote : ~vote;
+    }
+    const int leader = (lane == __ffs(peers) - 1) ? 1 : 0;
+    const int group = __popc(peers);
+    info[it] = dg | (__popc(peers & lt_mask) << 9) | (group << 15) | (leader << 22);
+    if (leader) cnt[warp][dg] += group;
     __syncwarp();
   }
   __syncthreads();
   {
-    const int dg = threadIdx.x;  // one thread per digit: exclusive scan over warps + global tile offset
-    int run = tile_off[(int64_t)dg * num_tiles + blockIdx.x];
+    const int dg = threadIdx.x;  // one thread per digit: exclusive scan over warps, then over digits
+    int run = 0;
 #pragma unroll
     for (int w = 0; w < kRadixThreads / 32; ++w) {
       int c = cnt[w][dg];
       cnt[w][dg] = run;
       run += c;
     }
+    int tile_total;
+    const int start = block_exclusive_scan(run, sw, tile_total);  // first staged slot of digit dg
+    gofs[dg] = tile_off[(int64_t)dg * num_tiles + blockIdx.x] - start;
+#pragma unroll
+    for (int w = 0; w < kRadixThreads / 32; ++w) cnt[w][dg] += start;
   }
   __syncthreads();
-  const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int it = 0; it < kRadixItems; ++it) {
-    unsigned m = __match_any_sync(0xffffffffu, d[it]);
-    int base = cnt[warp][d[it]];
+    const int dg = info[it] & 511;
+    const int base = cnt[warp][dg];
     __syncwarp();
-    if (lane == __ffs(m) - 1) cnt[warp][d[it]] = base + __popc(m);
+    if ((info[it] >> 22) & 1) cnt[warp][dg] = base + ((info[it] >> 15) & 127);
     __syncwarp();
-    if (d[it] != kRadixBins) {
-      int pos = base + __popc(m & lt_mask);
-      keys_out[pos] = k[it];
-      idx_out[pos] = id[it];
+    if (dg != kRadixBins) {
+      const int pos = base + ((info[it] >> 9) & 63);
+      skey[pos] = k[it];
+      sidx[pos] = idx_in[wbase + it * 32 + lane];   // payload fetched late: 16 fewer live registers through the ranking
     }
+  }
+  __syncthreads();
+  const int tile_n = (int)((n - tbase) < (int64_t)kRadixTile ? (n - tbase) : (int64_t)kRadixTile);
+  for (int i = threadIdx.x; i < tile_n; i += kRadixThreads) {
+    const uint64_t key = skey[i];
+    const int pos = gofs[(int)((key >> shift) & 255)] + i;
+    keys_out[pos] = key;
+    idx_out[pos] = sidx[i];
   }
 }
 
@@ -276,6 +310,8 @@ int bmkg_edge_sort(const int64_t* edge_index, int64_t E, int64_t N, int by_src, 
   int* offs = c.take<int>((size_t)tiles * kRadixBins + 1);
   int* sws = c.take<int>(scan_ws_ints((int64_t)tiles * kRadixBins));
 
+  if (cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRadixScatterSmem) != cudaSuccess)
+    return BMKG_ERR_LAUNCH;
   const int bits = key_bits(N);
   make_keys_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(edge_index, E, by_src, bits, k0, i0);
   const int passes = (2 * bits + 7) / 8;
@@ -283,7 +319,7 @@ int bmkg_edge_sort(const int64_t* edge_index, int64_t E, int64_t N, int by_src, 
     radix_hist_kernel<<<tiles, kRadixThreads, 0, st>>>(k0, E, 8 * p, hist, tiles);
     int rc = exclusive_scan(LoadI32{hist}, (int64_t)tiles * kRadixBins, offs, sws, st);
     if (rc != BMKG_OK) return rc;
-    radix_scatter_kernel<<<tiles, kRadixThreads, 0, st>>>(k0, i0, k1, i1, E, 8 * p, offs, tiles);
+    radix_scatter_kernel<<<tiles, kRadixThreads, kRadixScatterSmem, st>>>(k0, i0, k1, i1, E, 8 * p, offs, tiles);
     uint64_t* tk = k0; k0 = k1; k1 = tk;
     uint32_t* ti = i0; i0 = i1; i1 = ti;
   }
