@@ -179,6 +179,28 @@ def run_ours(args, rank, world, local_rank):
     class Batch:
         pass
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and not rowshard)
+    graphed = {}      # "resident" / "e2e" -> GraphedStep (captured lazily, after the eager warm-up)
+
+    def tail():
+        if world > 1 and not rowshard:  # DDP-equivalent: average parameter gradients over ranks (NCCL all-reduce, ~2 MB)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)   # gradient_clip_val=1.0 (train_gcl.py:99)
+        opt.step()
+
+    def graph_step(kind, batch):
+        """forward + backward replayed from a CUDA graph (biomedkg_b200/graphed.py); all-reduce / clip / Adam eager."""
+        gs = graphed[kind]
+        loss = gs(batch.x, batch.edge_index) if kind == "e2e" else gs()
+        tail()
+        return loss
+
     def step(batch):
         opt.zero_grad(set_to_none=True)
         if full_shard:
@@ -190,16 +212,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             loss = mod.training_step(batch)
             loss.backward()
-        if world > 1 and not rowshard:  # DDP-equivalent: average parameter gradients over ranks (NCCL all-reduce, ~2 MB)
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)   # gradient_clip_val=1.0 (train_gcl.py:99)
-        opt.step()
+        tail()
         return loss
 
     def barrier():
@@ -216,23 +229,52 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(res)
     barrier()
-    _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate_rows", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
-    _cabi.timings.clear()
+    run = step
+    if use_graph:
+        from biomedkg_b200.graphed import GraphedStep
+
+        opt.zero_grad(set_to_none=True)
+        graphed["resident"] = GraphedStep(mod, res.x, res.edge_index, resort=False)   # edge list fixed: sorted once, as in the eager loop
+        run = lambda bt: graph_step("resident", bt)  # noqa: E731
+        for _ in range(args.warmup):
+            run(res)
+        barrier()
+        # events cannot bracket kernels inside a replayed graph: per-kernel durations come from eager steps of the same
+        # training step, run right here (same clocks, same data), not from the replayed region
+        _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_gcn_aggregate_rows", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+        _cabi.timings.clear()
+        for _ in range(3):
+            step(res)
+        barrier()
+        kern_ms = {k: sum(a.elapsed_time(bb) for a, bb in v) / len(v) for k, v in _cabi.timings.items()}
+        kern_calls = {k: len(v) // 3 for k, v in _cabi.timings.items()}
+        _cabi.timed_entries.clear()
+        _cabi.timings.clear()
+        opt.zero_grad(set_to_none=True)
+        for _ in range(2):      # back to the replayed step (GraphedStep re-attaches its captured gradient buffers)
+            run(res)
+        barrier()
+    else:
+        _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate_rows", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+        _cabi.timings.clear()
     launches0 = _cabi.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        loss = step(res)
+        loss = run(res)
     e1.record()
     barrier()
     wall1 = time.time()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (_cabi.kernel_launches - launches0) // args.steps
-    kern_ms = {k: sum(a.elapsed_time(bb) for a, bb in v) / len(v) for k, v in _cabi.timings.items()}
-    kern_calls = {k: len(v) // args.steps for k, v in _cabi.timings.items()}
-    _cabi.timed_entries.clear()
+    if use_graph:
+        launches = graphed["resident"].launches_per_replay      # kernels of this package inside one replay of the captured step
+    else:
+        launches = (_cabi.kernel_launches - launches0) // args.steps
+        kern_ms = {k: sum(a.elapsed_time(bb) for a, bb in v) / len(v) for k, v in _cabi.timings.items()}
+        kern_calls = {k: len(v) // args.steps for k, v in _cabi.timings.items()}
+        _cabi.timed_entries.clear()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,6 +308,11 @@ def run_ours(args, rank, world, local_rank):
             ev.record(copy_stream)
         return bt, ev
 
+    if use_graph:
+        opt.zero_grad(set_to_none=True)
+        graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True)    # every step brings its own edge_index: sort captured too
+    run_e2e = (lambda bt: graph_step("e2e", bt)) if use_graph else step
+
     def e2e_loop(k):
         nxt = prefetch()
         losses_host = torch.empty(k, dtype=torch.float32).pin_memory()   # loss of every step lands here (async D2H per step)
@@ -276,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
             bt.edge_index.record_stream(torch.cuda.current_stream())
             if i + 1 < k:
                 nxt = prefetch()
-            losses_host[i:i + 1].copy_(step(bt).detach().reshape(1), non_blocking=True)   # device -> host read of the loss, every step
+            losses_host[i:i + 1].copy_(run_e2e(bt).detach().reshape(1), non_blocking=True)   # device -> host read of the loss, every step
         torch.cuda.current_stream().synchronize()
         return float(losses_host[-1])
 
@@ -293,7 +340,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = float(t.item())
     e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": (x_src.numel() * 4 + ei_host.numel() * 8) * (world if rowshard else 1),
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"}
+           "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
+                   + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if use_graph else "")}
 
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if rank != 0:
@@ -347,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "GCL nodes/sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if rowshard else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['desc']}", "nodes_per_gpu": N, "edges_per_gpu": E, "modalities": M, "in_dim": IN_DIM,
+        "config": {"workload": f"{args.config}: {cfg['desc']}", "nodes_per_gpu": N, "edges_per_gpu": E, "modalities": M, "in_dim": IN_DIM, "cuda_graph": bool(use_graph),
                    "hidden": HID, "conv_layers": LAYERS + 2, "tau": TAU, "parallelism": ((f"rowshard{world} (one graph; node rows split over ranks: fusion/GEMMs/aggregation/projector local, "
                                     f"all-gather of layer inputs and of Z, InfoNCE rows split, grads all-reduced)" if full_shard else
                                     f"rowshard{world} (one graph, replicated encoder, InfoNCE rows split over ranks, NCCL all-reduce of 1/R and dZ)")
@@ -391,6 +439,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="dp", choices=["dp", "rowshard"], help="multi-GPU mode (N>1)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the run (A/B of its overhead)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay forward+backward from a CUDA graph (auto: on unless --mode rowshard)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the end-to-end loop (default: --steps)")
     args = ap.parse_args()
     if args.impl == "ours" and args.config != "cfg5":      # W >= 3 (timing rules); cfg5 steps take seconds, 1 warm-up step is enough there

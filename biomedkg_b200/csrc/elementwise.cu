@@ -101,28 +101,30 @@ __global__ void __launch_bounds__(kEwThreads) relu_dropout_bwd_kernel(const __nv
   }
 }
 
-// out[c] = sum_b partial[b, c]: 32 columns x 8 interleaved row groups per CTA, fixed-order combine (deterministic)
-__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, int nb, int stride, int C, float* __restrict__ out) {
-  __shared__ float red[8][33];
+// out[c] = sum_b partial[b, c]: 32 columns x 32 interleaved row groups per CTA (1024 threads: the kernel is a chain of
+// dependent L2 loads, so more groups = a shorter chain), fixed-order combine (deterministic)
+constexpr int kFinishThreads = 1024;
+__global__ void __launch_bounds__(kFinishThreads) colsum_finish_kernel(const float* __restrict__ partial, int nb, int stride, int C, float* __restrict__ out) {
+  __shared__ float red[32][33];
   const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // 4 independent chains keep 4 loads in flight; combined in fixed order
   if (c < C) {
     int b = g;
-    for (; b + 24 < nb; b += 32) {
+    for (; b + 96 < nb; b += 128) {
       s0 += partial[(int64_t)b * stride + c];
-      s1 += partial[(int64_t)(b + 8) * stride + c];
-      s2 += partial[(int64_t)(b + 16) * stride + c];
-      s3 += partial[(int64_t)(b + 24) * stride + c];
+      s1 += partial[(int64_t)(b + 32) * stride + c];
+      s2 += partial[(int64_t)(b + 64) * stride + c];
+      s3 += partial[(int64_t)(b + 96) * stride + c];
     }
-    for (; b < nb; b += 8) s0 += partial[(int64_t)b * stride + c];
+    for (; b < nb; b += 32) s0 += partial[(int64_t)b * stride + c];
   }
   red[g][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (g == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][cl];
+    for (int k = 0; k < 32; ++k) t += red[k][cl];
     out[c] = t;
   }
 }
@@ -334,8 +336,8 @@ int bmkg_colsum_bf16(const void* x_bf16, const float* w1, const float* w2, int64
   for (int c0 = 0; c0 < C; c0 += 2048) {  // 2048-column slabs (one launch when C <= 2048)
     const int cw = (C - c0) < 2048 ? (C - c0) : 2048;
     colsum_bf16_partial_kernel<<<nb, kEwThreads, 0, st>>>(x + c0, C, w1, w2, N, cw, H, rows_per_cta, partial);
-    colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), 256, 0, st>>>(partial, nb, 2 * cw, cw, out1 + c0);
-    if (out2) colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), 256, 0, st>>>(partial + cw, nb, 2 * cw, cw, out2 + c0);
+    colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), kFinishThreads, 0, st>>>(partial, nb, 2 * cw, cw, out1 + c0);
+    if (out2) colsum_finish_kernel<<<(unsigned)ceil_div(cw, 32), kFinishThreads, 0, st>>>(partial + cw, nb, 2 * cw, cw, out2 + c0);
   }
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
@@ -365,7 +367,7 @@ int bmkg_relu_dropout_bwd(const void* gy_bf16, const void* y_bf16, float scale, 
   relu_dropout_bwd_kernel<<<nb, kEwThreads, (size_t)groups * C * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(gy_bf16), static_cast<const __nv_bfloat16*>(y_bf16), scale, N, C, rows_per_cta,
       static_cast<__nv_bfloat16*>(gpre_bf16), static_cast<float*>(ws));
-  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(static_cast<const float*>(ws), nb, C, C, dbias);
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), kFinishThreads, 0, st>>>(static_cast<const float*>(ws), nb, C, C, dbias);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
@@ -379,7 +381,7 @@ int bmkg_colsum(const float* z, const float* row_weight, int64_t N, int C, float
   const int rows_per_cta = (int)ceil_div(N, nb);
   colsum_partial_kernel<<<dim3(nb, (unsigned)ceil_div(C, 1024)), kEwThreads, 0, st>>>(z, row_weight, N, C, rows_per_cta,
                                                                                        static_cast<float*>(ws));
-  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(static_cast<const float*>(ws), nb, C, C, out);
+  colsum_finish_kernel<<<(unsigned)ceil_div(C, 32), kFinishThreads, 0, st>>>(static_cast<const float*>(ws), nb, C, C, out);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

@@ -61,6 +61,16 @@ class DeviceDraws:
         return float(torch.rand(1).item())
 
 
+class GraphSafeDraws(DeviceDraws):
+    """Draws for a CUDA-graph-captured step (biomedkg_b200/graphed.py).  A captured kernel's scalar arguments are frozen,
+    so the per-call dropout seed of ``DeviceDraws`` would replay the same mask forever; here the encoder dropout mask is
+    drawn by torch's device generator (whose Philox offset a captured graph advances on every replay) and handed to the
+    aggregation epilogue as an explicit keep mask."""
+
+    def dropout(self, shape, p, device):
+        return 0, torch.rand(shape, device=device) >= p
+
+
 class ReplayDraws:
     """Replays (kind, value) records, e.g. the ``draws`` list of a golden fixture."""
 

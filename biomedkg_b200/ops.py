@@ -65,12 +65,13 @@ class _Sorted:
 class SortedGraph:
     """edge_index sorted once by (dst,src) and by (src,dst); parent of every view."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, assume_hubs: bool | None = None):
         _need_cuda(edge_index)
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
         self.edge_index = edge_index.contiguous()
         self.N, self.E = int(num_nodes), int(edge_index.size(1))
+        self._full_view: dict = {}
         dev = edge_index.device
         ws = _ws(lib.bmkg_edge_sort_workspace_bytes(self.N, self.E), dev)
         self.by = []
@@ -86,7 +87,9 @@ class SortedGraph:
             self.by.append(s)
         # A view only removes edges, so if no raw row (+1 self-loop) exceeds the split-row threshold no view can have hub rows
         # and the aggregation kernels skip their hub pre-pass launches.  One host read per new edge_index tensor.
-        if self.E > HUB_THRESHOLD:
+        if assume_hubs is not None:      # no host read (CUDA-graph capture): the caller decides whether hub pre-passes run
+            self.hub_possible = bool(assume_hubs)
+        elif self.E > HUB_THRESHOLD:
             d0 = (self.by[0].rowptr_raw[1:] - self.by[0].rowptr_raw[:-1]).max()
             d1 = (self.by[1].rowptr_raw[1:] - self.by[1].rowptr_raw[:-1]).max()
             self.hub_possible = int(torch.maximum(d0, d1).item()) + 1 > HUB_THRESHOLD
@@ -94,6 +97,11 @@ class SortedGraph:
             self.hub_possible = False
 
     def view(self, keep: torch.Tensor | None = None, want_perm: bool = False) -> "GraphView":
+        if keep is None:   # the un-augmented view depends on the edge list only: build it once per sorted graph
+            cached = self._full_view.get(want_perm)
+            if cached is None:
+                cached = self._full_view[want_perm] = GraphView(self, None, want_perm)
+            return cached
         return GraphView(self, keep, want_perm)
 
 
@@ -139,11 +147,14 @@ class GraphView:
 
 
 _GRAPH_CACHE: dict = {}
+_CAPTURE_RESORT = False   # set by graphed.GraphedStep while it captures a step that includes the edge sort
 
 
 def sorted_graph(edge_index: torch.Tensor, num_nodes: int, cache: bool = True) -> SortedGraph:
     """Sort once per (tensor identity, version): full-graph training reuses the
     same edge_index tensor every step, so the radix sort runs once."""
+    if _CAPTURE_RESORT:   # inside a captured step that re-sorts its static edge_index buffer on every replay
+        return SortedGraph(edge_index, num_nodes, assume_hubs=edge_index.size(1) > HUB_THRESHOLD)
     if not cache:
         return SortedGraph(edge_index, num_nodes)
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), edge_index.device)
