@@ -234,7 +234,13 @@ def run_ours(args, rank, world, local_rank):
         from biomedkg_b200.graphed import GraphedStep
 
         opt.zero_grad(set_to_none=True)
-        graphed["resident"] = GraphedStep(mod, res.x, res.edge_index, resort=False)   # edge list fixed: sorted once, as in the eager loop
+        try:
+            graphed["resident"] = GraphedStep(mod, res.x, res.edge_index, resort=False)   # edge list fixed: sorted once, as in the eager loop
+        except Exception as exc:  # noqa: BLE001 - a failed capture must not cost the measurement: fall back to eager launches
+            print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
+    if use_graph:
         run = lambda bt: graph_step("resident", bt)  # noqa: E731
         for _ in range(args.warmup):
             run(res)
@@ -308,10 +314,16 @@ def run_ours(args, rank, world, local_rank):
             ev.record(copy_stream)
         return bt, ev
 
-    if use_graph:
+    e2e_graph = use_graph
+    if e2e_graph:
         opt.zero_grad(set_to_none=True)
-        graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True)    # every step brings its own edge_index: sort captured too
-    run_e2e = (lambda bt: graph_step("e2e", bt)) if use_graph else step
+        try:
+            graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True)    # every step brings its own edge_index: sort captured too
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUDA-graph capture of the end-to-end step failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            e2e_graph = False
+            torch.cuda.synchronize()
+    run_e2e = (lambda bt: graph_step("e2e", bt)) if e2e_graph else step
 
     def e2e_loop(k):
         nxt = prefetch()
@@ -341,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": (x_src.numel() * 4 + ei_host.numel() * 8) * (world if rowshard else 1),
            "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
            "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
-                   + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if use_graph else "")}
+                   + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if e2e_graph else "")}
 
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if rank != 0:

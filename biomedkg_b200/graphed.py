@@ -48,7 +48,8 @@ class GraphedStep:
             p.grad = None
         launches0 = _launch_counter()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: helper threads of the process (NCCL watchdog, clock samplers) may make CUDA calls during the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._fwd_bwd()
         self.launches_per_replay = _launch_counter() - launches0
         self.params = params
