@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -80,11 +80,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0=None, t1=None):
-        """Summarise the samples that arrived inside [t0, t1] (the timed region)."""
+    def stop(self, *windows):
+        """Summarise the samples that arrived inside the given (t0, t1) wall-clock windows (the timed regions)."""
         if self.proc:
             self.proc.terminate()
-        rows = [r for ts, r in self.rows if len(r) >= 9 and (t0 is None or t0 <= ts <= t1 + 0.15)]
+        rows = [r for ts, r in self.rows if len(r) >= 9 and (not windows or any(t0 <= ts <= t1 + 0.05 for t0, t1 in windows))]
         sm = sorted(int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit())
         mx = max((int(float(r[2])) for r in rows if r[2].replace(".", "").isdigit()), default=None)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -342,10 +342,12 @@ def run_ours(args, rank, world, local_rank):
     e2e_loop(max(1, min(2, k2_warm)))
     barrier()
     k2 = max(1, args.e2e_steps if args.e2e_steps is not None else args.steps)
+    wall2 = time.time()
     e0.record()
     e2e_loop(k2)
     e1.record()
     barrier()
+    wall3 = time.time()
     t = torch.tensor([e0.elapsed_time(e1) / k2], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -355,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
            "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
                    + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if e2e_graph else "")}
 
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    clocks = sampler.stop((wall0, wall1), (wall2, wall3)) if rank == 0 else None    # both timed regions (device-resident and end-to-end)
     if rank != 0:
         return
     # ---------------- roofline of the dominant kernel ----------------
@@ -443,7 +445,7 @@ def _emit(line: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))

@@ -55,3 +55,50 @@ elif what in ("gcn", "gat", "gcn_powerlaw"):
     ms = e0.elapsed_time(e1) / 10
     byts = nnz * (256 * 2 + 4) + n * 256 * 2 + 4 * (n + 1)
     print(f"gcn_aggregate N={n} nnz={nnz}: {ms*1e3:.1f} us, {byts/ms/1e6:.0f} GB/s algorithmic")
+if what == "redaf":   # python tools/prof_kernels.py redaf N [iters] [M]: fused ReDAF epilogue, forward and backward, E = 768
+    M = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    E = 768
+    t = torch.randn(n, M, E, device=dev).to(torch.bfloat16)
+    bias = torch.randn(E, device=dev, requires_grad=True)
+    gate = (torch.rand(M, E, device=dev) + 0.5).requires_grad_(True)
+    tt = t.float().requires_grad_(True)
+
+    def run():
+        o = ops.redaf_fuse(tt.to(torch.bfloat16), bias, gate, 0.1, 1234, None)
+        o.backward(torch.ones_like(o))
+
+    from biomedkg_b200 import _cabi
+
+    for _ in range(iters):
+        run()
+    torch.cuda.synchronize()
+    _cabi.timed_entries.update({"bmkg_redaf_fwd", "bmkg_redaf_bwd"})
+    _cabi.timings.clear()
+    for _ in range(5):
+        run()
+    torch.cuda.synchronize()
+    tm = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _cabi.timings.items()}
+    fb = n * M * E * 2 + n * E * 4
+    bb = n * E * 4 + 2 * n * M * E * 2
+    print(f"redaf N={n} M={M} E={E}: fwd {tm['bmkg_redaf_fwd']:.3f} ms = {fb / tm['bmkg_redaf_fwd'] / 1e6:.0f} GB/s algorithmic; "
+          f"bwd {tm['bmkg_redaf_bwd']:.3f} ms = {bb / tm['bmkg_redaf_bwd'] / 1e6:.0f} GB/s algorithmic")
+elif what == "star":  # python tools/prof_kernels.py star N [iters] [E]: export-path star aggregation, C = 256, rows > L2 when N >= 1M
+    e = int(sys.argv[4]) if len(sys.argv) > 4 else n * 30
+    ei = torch.randint(0, n, (2, e), device=dev)
+    view = ops.SortedGraph(ei, n).view(None)
+    leaf = torch.randn(n, 256, device=dev).to(torch.bfloat16)
+    seed = torch.randn(n, 256, device=dev).to(torch.bfloat16)
+    bias = torch.zeros(256, device=dev)
+    for _ in range(iters):
+        ops.gcn_star_aggregate(view.rowptr, view.colind, view.dis, leaf, seed, bias, relu=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.gcn_star_aggregate(view.rowptr, view.colind, view.dis, leaf, seed, bias, relu=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    nnz = int(view.nnz.item())
+    byts = nnz * (256 * 2 + 4) + n * 256 * 2 * 2 + 4 * (n + 1)
+    print(f"star N={n} nnz={nnz}: {ms:.3f} ms = {byts / ms / 1e6:.0f} GB/s algorithmic")
