@@ -39,6 +39,24 @@ def hash_keep_mask(seed: int, numel: int, p: float) -> torch.Tensor:
     return torch.from_numpy(u >= thr)
 
 
+def hash_keep_mask16(seed: int, numel: int, p: float) -> torch.Tensor:
+    """Host mirror of the ReDAF kernels' stream (csrc/redaf.cu): one hash_u32 per two consecutive elements,
+    keep[i] = 16-bit half (i & 1) of hash_u32(seed, i >> 1) >= p * 2^16."""
+    import numpy as np
+
+    idx = np.arange((numel + 1) // 2, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed & _MASK64)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    h = (z >> np.uint64(32)).astype(np.uint64)
+    halves = np.stack([h & np.uint64(0xFFFF), h >> np.uint64(16)], axis=1).reshape(-1)[:numel]
+    return torch.from_numpy(halves >= np.uint64(int(p * 65536.0)))
+
+
 class DeviceDraws:
     def __init__(self):
         self._counter = 0

@@ -195,7 +195,8 @@ int bmkg_fusion_attn_bwd(const void* qkv_bf16, const float* qkv_bias, const floa
  * biomedkg/utils/fusion.py:70-90 after the transform GEMM: out[n] = mean_m relu(dropout_p(relu(t[n,m] + bias) * gate[m])),
  * gate[m] = modal_weights[m] * sigmoid(relational_context_layer(0.2 * 1)) (fusion.py:54-56,82-84) computed by the caller.
  * t bf16 [N,M,E] = bias-free x W^T; bias fp32 [E]; gate fp32 [M,E]; out fp32 [N,E]; M <= 4, E % 8 == 0.
- * Dropout: drop_keep uint8 [N,M,E] if given, else the counter hash on (drop_seed, flat index), else none (drop_p = 0).
+ * Dropout: drop_keep uint8 [N,M,E] if given, else a counter hash (element i is kept iff 16-bit half (i & 1) of
+ * hash_u32(drop_seed, i >> 1) >= drop_p * 2^16), else none (drop_p = 0).
  * Backward: dt bf16 [N,M,E] (gradient w.r.t. t, hence also w.r.t. t + bias) and per-CTA partial sums
  * dgate_partial fp32 [bmkg_redaf_partial_rows(N,E), M, E] whose column sums (bmkg_colsum) are d gate. */
 int64_t bmkg_redaf_partial_rows(int64_t num_nodes, int embed);
