@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=10)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--log", default=None)
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay forward+backward from a CUDA graph (graphed.GraphedStep; GRACE only, fixed full graph)")
     a = ap.parse_args()
 
     torch.manual_seed(a.seed)
@@ -56,12 +58,22 @@ def main():
     opt = torch.optim.Adam(mod.model.parameters(), lr=a.learning_rate)
     sched = mod._get_scheduler(opt, num_training_steps=a.epochs)
     out = open(a.log, "a") if a.log else None
+    graphed = None
+    if a.cuda_graph:
+        if a.model != "grace":
+            raise SystemExit("--cuda-graph: DGI / GGD draw from the CPU generator inside the step; only GRACE is capturable")
+        from .graphed import GraphedStep
+
+        graphed = GraphedStep(mod, Batch.x, Batch.edge_index, resort=False)
     for epoch in range(a.epochs):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        loss = mod.training_step(Batch)
-        loss.backward()
+        if graphed is not None:
+            loss = graphed()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = mod.training_step(Batch)
+            loss.backward()
         torch.nn.utils.clip_grad_norm_(mod.model.parameters(), 1.0)
         opt.step()
         sched.step()
