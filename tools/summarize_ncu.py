@@ -58,9 +58,13 @@ def summarize_launches(csv_path, out, steps_in_file):
         tot[n] += ms
         cnt[n] += 1
     S = sum(tot.values())
+    nb = sum(c for n, c in cnt.items() if "infonce_bwd_kernel" in n)
+    if nb:
+        steps_in_file = nb      # one InfoNCE backward per training step: eager warm-up, graph warm-up, replays, end-to-end
     with open(out, "w") as f:
-        f.write(f"# launch list of `bench.py --steps 2 --warmup 3` under ncu --metrics gpu__time_duration.sum --clock-control none\n")
-        f.write(f"# {len(rows)} launches over {steps_in_file} steps (3 warm-up + 2 timed + 1+1 end-to-end); per-launch times are cold-cache and\n")
+        f.write(f"# launch list of `bench.py --steps 2 --warmup 3 --no-cpu-baseline` under ncu --metrics gpu__time_duration.sum --clock-control none\n")
+        f.write(f"# {len(rows)} launches over {steps_in_file} training steps (one InfoNCE backward each).  Under the profiler bench.py's CUDA-graph\n"
+                f"# capture is not in play (the list is the eager sequence of the same kernels); per-launch times are cold-cache and\n")
         f.write(f"# serialised, so compare SHARES.  total {S:.2f} ms = {S / steps_in_file:.2f} ms/step, {len(rows) / steps_in_file:.0f} launches/step\n\n")
         f.write(f"{'ms/step':>9s} {'launches/step':>14s} {'share':>7s}  kernel\n")
         for n, v in sorted(tot.items(), key=lambda x: -x[1]):
