@@ -29,6 +29,17 @@ struct SortedFlag {
     return keep ? (keep[perm[k]] != 0) : 1;
   }
 };
+// same flag, recorded as a byte while the scan's first pass evaluates it: the keep[perm[k]] lookup is a random 1-byte gather
+// (a 32-byte sector per edge), so it is done once and the down-sweep and the compaction read the byte / the scanned positions
+struct SortedFlagStore {
+  SortedFlag f;
+  uint8_t* out;
+  __device__ int operator()(int64_t k) const {
+    const int v = f(k);
+    out[k] = (uint8_t)v;
+    return v;
+  }
+};
 // flag of original edge e
 struct OrigFlag {
   const int64_t* src;
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(SortedFlag flag, cons
                                                            int32_t* __restrict__ colind, int32_t* __restrict__ perm) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= E) return;
-  if (!flag(k)) return;
+  if (pos[k + 1] == pos[k]) return;   // dropped (pos is the exclusive scan of the flags, E + 1 entries)
   const int row = flag.major[k], c = flag.minor[k];
   const int o = pos[k] + row + (c > row ? 1 : 0);
   colind[o] = c;
@@ -335,6 +346,7 @@ size_t bmkg_csr_filter_workspace_bytes(int64_t N, int64_t E) {
   c.take<int>(E + 1);
   c.take<int>(E + 1);
   c.take<int>(scan_ws_ints(E));
+  c.take<uint8_t>(E + 1);
   (void)N;
   return c.used();
 }
@@ -353,8 +365,9 @@ int bmkg_csr_filter(const int32_t* major_sorted, const int32_t* minor_sorted, co
   int* pos = c.take<int>(E + 1);
   int* rank = c.take<int>(E + 1);
   int* sws = c.take<int>(scan_ws_ints(E));
+  uint8_t* fbytes = c.take<uint8_t>(E + 1);
   SortedFlag sf{major_sorted, minor_sorted, perm_sorted, keep};
-  int rc = exclusive_scan(sf, E, pos, sws, st);
+  int rc = exclusive_scan2(SortedFlagStore{sf, fbytes}, LoadU8{fbytes}, E, pos, sws, st);
   if (rc != BMKG_OK) return rc;
   if (perm && E > 0) {
     rc = exclusive_scan(OrigFlag{edge_index, edge_index + E, keep}, E, rank, sws, st);

@@ -16,6 +16,10 @@ struct LoadI32 {
   const int32_t* p;
   __device__ int operator()(int64_t i) const { return p[i]; }
 };
+struct LoadU8 {
+  const uint8_t* p;
+  __device__ int operator()(int64_t i) const { return p[i]; }
+};
 __device__ __forceinline__ int block_exclusive_scan(int thread_sum, int* smem_warp, int& block_total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = thread_sum;
@@ -121,6 +125,17 @@ __global__ void __launch_bounds__(kScanThreads) scan_down_kernel(F f, int64_t n,
 }
 
 inline size_t scan_ws_ints(int64_t n) { return (size_t)ceil_div(n + 1, kScanTile) + 1; }
+
+// two-functor form: `fr` feeds the tile sums (and may record what it computed), `fd` feeds the down-sweep
+template <class FR, class FD>
+static int exclusive_scan2(FR fr, FD fd, int64_t n, int* out, int* ws_block_sums, cudaStream_t st) {
+  const int nb = (int)ceil_div(n + 1, kScanTile);
+  scan_reduce_kernel<FR><<<nb, kScanThreads, 0, st>>>(fr, n, ws_block_sums);
+  scan_block_sums_kernel<<<1, 1024, 0, st>>>(ws_block_sums, nb, nullptr);
+  scan_down_kernel<FD><<<nb, kScanThreads, 0, st>>>(fd, n, ws_block_sums, out);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
 
 template <class F>
 static int exclusive_scan(F f, int64_t n, int* out, int* ws_block_sums, cudaStream_t st) {
