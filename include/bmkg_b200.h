@@ -1,7 +1,7 @@
 /* bmkg_b200 - C-ABI of the B200-native GCL training-step kernels.
  *
  * The reference (HySonLab/BioMedKG) has no FFI: its extension seam is the
- * torch.nn.Module surface (biomedkg/model/*, biomedkg/utils/fusion.py,
+ * torch.nn.Module surface (biomedkg/model/ (all files), biomedkg/utils/fusion.py,
  * biomedkg/gcl_module.py) and every kernel below replaces a third-party library
  * call reached from that surface.  Each entry point cites the reference call
  * site it serves.  INTEGRATION.md shows the ctypes binding a maintainer adds.

@@ -122,3 +122,24 @@ def test_lightning_checkpoint_layout_loads_reference_state_dict(libpath, golden_
     mod.save_checkpoint(path)
     again = cls.load_from_checkpoint(path)
     assert {k: again.hparams[k] for k in hp} == hp
+
+
+def test_header_is_plain_c_and_links(libpath, tmp_path):
+    """The boundary is a C ABI: include/bmkg_b200.h must compile as C99 (no C++-isms, no torch types) and a C program must
+    link against the shared library and call a host-only entry point (no GPU needed)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "bmkg_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%d %lld\\n", bmkg_abi_version(), (long long)bmkg_infonce_padded_rows(100)); return 0; }\n')
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(libpath)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", str(src), "-I", os.path.join(root, "include"), "-L", libdir,
+                        "-lbmkg_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split()[1] == "256" and int(out.stdout.split()[0]) >= 1
