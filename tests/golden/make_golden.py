@@ -130,6 +130,38 @@ def graph(n, e, seed, self_loops=3, dups=5):
     return ei
 
 
+def redaf_train_fixture(ref_fusion, IN=32):
+    """The reference's own ReDAF (utils/fusion.py:34-90) in TRAINING mode.  Its nn.Dropout draws from torch's generator
+    and keeps no record, so the instance attribute `dropout` (not the source) is swapped for a module that draws the
+    same Bernoulli(1-p) keep mask with torch.rand_like and remembers it; everything else is the reference's arithmetic."""
+
+    class _RecordingDropout(torch.nn.Module):
+        def __init__(self, p):
+            super().__init__()
+            self.p, self.mask = p, None
+
+        def forward(self, x):
+            self.mask = torch.rand_like(x) >= self.p
+            return x * self.mask.to(x.dtype) / (1.0 - self.p)
+
+    torch.manual_seed(31)
+    red = ref_fusion.ReDAF(IN).train()
+    with torch.no_grad():
+        red.modal_weights.normal_(1.0, 0.5)               # some negative gates: the second ReLU must cut them
+        red.transform_layer.bias.normal_(0.0, 0.2)
+    red.dropout = _RecordingDropout(red.dropout.p)
+    x = torch.randn(257, 2, IN)
+    x = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16).float().requires_grad_(True)   # representable on the device as is
+    w = torch.randn(257, IN)
+    out = red(x)
+    (out * w).sum().backward()
+    torch.save({"x": x.detach(), "w": w, "state_dict": {k: v.clone() for k, v in red.state_dict().items()},
+                "mask": red.dropout.mask, "p": red.dropout.p, "out": out.detach(), "x_grad": x.grad.clone(),
+                "grads": {k: p.grad.clone() for k, p in red.named_parameters() if p.grad is not None}},
+               os.path.join(HERE, "fusion_redaf_m2_train.pt"))
+    print("fusion_redaf_m2_train: out norm", float(out.norm()))
+
+
 def main():
     _install_shims()
     sys.path.insert(0, REF)
@@ -137,6 +169,10 @@ def main():
     import biomedkg.model.encoder as ref_enc
     import biomedkg.model.gcl as ref_gcl
     import biomedkg.utils.fusion as ref_fusion
+
+    only_new = "--only-redaf-train" in sys.argv      # added after the first batch of fixtures: leaves the others untouched
+    if only_new:
+        redaf_train_fixture(ref_fusion)
 
     _patch_draw_sites(ref_gcl)
 
@@ -158,9 +194,24 @@ def main():
     IN, HID, L = 32, 64, 2
     out = {}
 
-    def run(name, cls, n, e, seed, fuse, M, train=True, dtype=torch.float64):
+    class _LoggedDropout(torch.nn.Module):
+        """stands in for the nn.Dropout INSTANCE of a reference ReDAF (the source is untouched): same Bernoulli(1-p) keep
+        mask, drawn with torch.rand_like and logged like every other draw"""
+
+        def __init__(self, p):
+            super().__init__()
+            self.p = p
+
+        def forward(self, x):
+            if not self.training:
+                return x
+            return x * DRAWS.dropout_mask(x, self.p).to(x.dtype) / (1.0 - self.p)
+
+    def run(name, cls, n, e, seed, fuse, M, train=True, dtype=torch.float64, log_fuser_dropout=False):
         torch.manual_seed(seed)
         mod = cls(in_dim=IN, hidden_dim=HID, out_dim=HID, num_hidden_layers=L, fuse_method=fuse)
+        if log_fuser_dropout:
+            mod.modality_transform.dropout = _LoggedDropout(mod.modality_transform.dropout.p)
         mod.to(dtype)
         mod.train(train)
         g = torch.Generator().manual_seed(seed + 1)
@@ -193,6 +244,11 @@ def main():
         torch.save(fx, os.path.join(HERE, name + ".pt"))
         out[name] = float(loss)
 
+    if only_new:
+        run("grace_redaf_train", ref_mod.GRACEModule, 80, 300, 17, "redaf", 2, train=True, dtype=torch.float32, log_fuser_dropout=True)
+        print({k: round(v, 6) for k, v in out.items()})
+        return
+    run("grace_redaf_train", ref_mod.GRACEModule, 80, 300, 17, "redaf", 2, train=True, dtype=torch.float32, log_fuser_dropout=True)
     run("grace_none", ref_mod.GRACEModule, 96, 400, 10, "none", 0)
     run("grace_mean2", ref_mod.GRACEModule, 80, 300, 11, None, 2)
     run("grace_attention", ref_mod.GRACEModule, 72, 260, 12, "attention", 2)
@@ -220,6 +276,8 @@ def main():
     xg = torch.randn(n, IN, dtype=torch.float64)
     with torch.no_grad():
         torch.save({"x": xg, "edge_index": ei, "state_dict": enc.state_dict(), "out": enc(xg, ei)}, os.path.join(HERE, "gcn_encoder_eval.pt"))
+
+    redaf_train_fixture(ref_fusion)
 
     for k, v in out.items():
         print(f"{k}: loss={v:.9f}")

@@ -319,3 +319,27 @@ def test_redaf_hashed_dropout_matches_host_mirror_and_eval_is_deterministic():
         outs.append((tt.grad, bb.grad, gg.grad))
     for u, v in zip(*outs):
         assert torch.equal(u, v)
+
+
+def test_redaf_training_reference_golden(golden_dir):
+    """ReDAF in training mode against the vectors the reference's own module produced (tests/golden/make_golden.py,
+    dropout mask recorded there and replayed here): output <= 1e-2, gradients within the bf16 ReLU-flip bound."""
+    import os
+
+    from biomedkg_b200.draws import ReplayDraws
+    from biomedkg_b200.utils.fusion import ReDAF
+
+    fx = torch.load(os.path.join(golden_dir, "fusion_redaf_m2_train.pt"), weights_only=False)
+    red = ReDAF(fx["x"].size(-1)).to(DEV).train()
+    red.load_state_dict(fx["state_dict"])
+    red.draws = ReplayDraws([("dropout_mask", fx["mask"])], DEV)
+    x = fx["x"].to(DEV).requires_grad_(True)
+    out = red(x)
+    (out * fx["w"].to(DEV)).sum().backward()
+    assert rel_err(out, fx["out"]) < 1e-2
+    assert rel_err(x.grad, fx["x_grad"]) < 6e-2
+    for k, p in red.named_parameters():
+        if k in fx["grads"]:
+            assert rel_err(p.grad, fx["grads"][k]) < 6e-2, k
+        else:
+            assert p.grad is None, k

@@ -12,7 +12,7 @@ import torch
 from oracle import models as om
 from oracle import pyg, pygcl
 
-MODULE_FIXTURES = ["grace_none", "grace_mean2", "grace_attention", "dgi_none", "ggd_none_a", "ggd_none_b", "ggd_redaf"]
+MODULE_FIXTURES = ["grace_none", "grace_mean2", "grace_attention", "dgi_none", "ggd_none_a", "ggd_none_b", "ggd_redaf", "grace_redaf_train"]
 
 
 def _load(golden_dir, name):
@@ -55,6 +55,25 @@ def test_fusion_goldens(golden_dir):
     red = om.ReDAF(fx["x"].size(-1)).eval()
     red.load_state_dict(fx["state_dict"])
     assert torch.allclose(red(fx["x"]), fx["out"], atol=1e-6)
+
+
+def test_redaf_training_golden(golden_dir):
+    """The reference's ReDAF in training mode (dropout mask recorded by the generator): forward and every gradient."""
+    fx = _load(golden_dir, "fusion_redaf_m2_train")
+    red = om.ReDAF(fx["x"].size(-1))
+    red.load_state_dict(fx["state_dict"])
+    red.train()
+    red.draws = om.ReplayDraws([("dropout_mask", fx["mask"])])
+    x = fx["x"].clone().requires_grad_(True)
+    out = red(x)
+    (out * fx["w"]).sum().backward()
+    assert torch.allclose(out, fx["out"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(x.grad, fx["x_grad"], rtol=1e-4, atol=1e-6)
+    for k, p_ in red.named_parameters():
+        if k in fx["grads"]:
+            assert torch.allclose(p_.grad, fx["grads"][k], rtol=1e-4, atol=1e-5), k
+        else:
+            assert p_.grad is None, k
 
 
 def test_gcn_encoder_golden(golden_dir):
