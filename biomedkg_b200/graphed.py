@@ -26,6 +26,12 @@ from .draws import GraphSafeDraws, set_draws
 class GraphedStep:
     def __init__(self, module, x: torch.Tensor, edge_index: torch.Tensor, resort: bool = False, warmup: int = 3,
                  loss_fn=None):
+        from .model.gcl import GRACE
+
+        if loss_fn is None and not isinstance(getattr(module, "model", None), GRACE):
+            # DGI's permutation and GGD's coin come from the CPU generator (model/gcl.py:17,66): a captured graph would
+            # replay the one permutation / branch it saw at capture time
+            raise NotImplementedError("GraphedStep captures the GRACE step; DGI / GGD draw from the CPU generator inside the step")
         ops._need_cuda(x, edge_index)
         self.module = module
         self.resort = bool(resort)

@@ -71,3 +71,18 @@ def test_lightning_stand_in_captures_outermost_init_kwargs():
     m = b.GGDModule(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2, fuse_method="redaf", learning_rate=5e-4)
     assert m.hparams["learning_rate"] == 5e-4 and m.hparams["fuse_method"] == "redaf" and m.hparams["in_dim"] == 32
     assert "model" not in m.hparams and "embed_dim" not in m.hparams        # BaseGCL's own arguments are not the checkpoint's
+
+
+def test_graphed_step_refuses_objectives_with_host_side_draws():
+    import pytest
+
+    import biomedkg_b200 as b
+    from biomedkg_b200.graphed import GraphedStep
+
+    for cls in (b.DGIModule, b.GGDModule):
+        m = cls(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2)
+        with pytest.raises(NotImplementedError):
+            GraphedStep(m, torch.zeros(8, 32), torch.zeros(2, 4, dtype=torch.int64))
+    with pytest.raises(RuntimeError):      # GRACE passes the objective check and then fails loudly on CPU tensors (no CPU path)
+        GraphedStep(b.GRACEModule(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2), torch.zeros(8, 32),
+                    torch.zeros(2, 4, dtype=torch.int64))
