@@ -239,6 +239,268 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ----------------------------------------------------------------------------
+// forward on the upper triangle of the Gram matrix  (BMKG_INFONCE_FWD=tri; full-range launches only)
+// ----------------------------------------------------------------------------
+// E = 2^S is symmetric, so only tiles (rb, cb) with cb >= rb are computed: an off-diagonal tile adds its ROW sums to the
+// rows of block rb (registers, as in the kernel above) and its COLUMN sums to the rows of block cb.  The column sums come
+// from the tensor core with the column index on the TMEM lanes: the softmax warpgroup stores E (bf16) in shared memory in
+// the MN-major 128-byte-swizzle layout (thread i writes its own row), and one small MMA
+//     D2[128 x 16] = E^T[M = j, K = i] * Ones[K = i, N = 16]              (A = E buffer read MN-major, B = constant ones)
+// leaves column sum j in lane j (0.5 MFLOP against 8.4 for the S tile); thread j adds it to a slot private to
+// (CTA, warpgroup) that the finaliser sums in fixed order (deterministic, no atomics).  8 N^2 D -> ~4.3 N^2 D executed and
+// half the ex2 work.  TMEM: [0,128) stationary rows, [128,384) S ring (2), [384,400) / [400,416) D2 of warpgroup 0 / 1.
+// Tile t of a CTA (running count) uses S buffer, E buffer and D2 number t & 1 and is handled by warpgroup t & 1.
+constexpr int kTriStages = 2;
+constexpr int kTriEBytes = kBM * kBN * 2;    // one E tile, bf16
+constexpr int kTriOnesBytes = 16 * 128 * 2;  // B operand of the column-sum MMA: 16 x 128 bf16 ones (K-major, two 64-wide panels)
+constexpr uint32_t kTriColS = 128, kTriColD2 = 384;
+constexpr size_t kTriSmemBytes =
+    1024 + (size_t)kFwdPanelBytes * kMaxPanels * kTriStages + 2 * (size_t)kTriEBytes + kTriOnesBytes + 256;
+
+// work item -> (row block, column chunk, tile range).  Row blocks are dealt to the CTAs in snake order per round so that
+// long (small rb) and short (large rb) strips of the triangle mix on every CTA.  Every role calls this with the same item.
+__device__ __forceinline__ void tri_item(int item, const Schedule& sch, int G, int& rb, int& cc, int& lo, int& hi) {
+  cc = item / sch.nrb;
+  const int r = item % sch.nrb;
+  const int round = r / G;
+  int pos = r % G;
+  if (round < sch.nrb / G && (round & 1)) pos = G - 1 - pos;
+  rb = sch.rb0 + round * G + pos;
+  const int t0 = cc * sch.tiles_per_chunk;
+  hi = min(sch.ntiles, t0 + sch.tiles_per_chunk);
+  lo = max(t0, rb);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_fwd_tri_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
+                       const __nv_bfloat16* __restrict__ z, float* __restrict__ partial) {
+  constexpr int D = NP * kPanelElems;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  uint8_t* sB = smem;
+  uint8_t* sE = sB + (size_t)kFwdPanelBytes * kMaxPanels * kTriStages;  // two E tiles, 1024-byte aligned
+  uint8_t* sOnes = sE + 2 * (size_t)kTriEBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kTriOnesBytes);
+  uint64_t* full = bars;                    // [kTriStages]
+  uint64_t* empty = full + kTriStages;      // [kTriStages]
+  uint64_t* a_full = empty + kTriStages;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* tfull = a_empty + 1;            // [2] S tile ready
+  uint64_t* tempty = tfull + 2;             // [2] S tile drained to registers (4 warp arrivals)
+  uint64_t* e_full = tempty + 2;            // [2] E tile written by the warpgroup (4 warp arrivals)
+  uint64_t* e_empty = e_full + 2;           // [2] column-sum MMA has read the E tile
+  uint64_t* d_full = e_empty + 2;           // [2] column sums in TMEM
+  uint64_t* d_empty = d_full + 2;           // [2] column sums read back (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTriStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    ptx::mbar_init(a_full, 4);
+    ptx::mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4);
+      ptx::mbar_init(&e_full[b], 4); ptx::mbar_init(&e_empty[b], 1);
+      ptx::mbar_init(&d_full[b], 1); ptx::mbar_init(&d_empty[b], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmap);
+  }
+  for (int i = threadIdx.x; i < kTriOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
+  ptx::fence_proxy_async_smem();
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = sch.nrb * sch.nchunks;
+  const uint32_t tile_bytes = (uint32_t)NP * kFwdPanelBytes;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer ----------------
+      int stage = 0;
+      uint32_t sphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += G) {
+        int rb, cc, lo, hi;
+        tri_item(item, sch, G, rb, cc, lo, hi);
+        for (int ct = lo; ct < hi; ++ct) {
+          ptx::mbar_wait(&empty[stage], sphase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          uint8_t* dst = sB + (size_t)stage * kFwdPanelBytes * kMaxPanels;
+          for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kFwdPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          if (++stage == kTriStages) { stage = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {  // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);   // S = A(tmem) B^T
+    constexpr uint32_t idesc_c = ptx::idesc_bf16_f32(kBM, 16, 1, 0);    // D2 = E^T(smem, MN-major) Ones
+    const uint64_t ones_desc = ptx::smem_desc_sw128(ptx::smem_u32(sOnes), 16, 1024);
+    uint64_t e_desc[2];
+    for (int b = 0; b < 2; ++b) e_desc[b] = ptx::smem_desc_sw128(ptx::smem_u32(sE + (size_t)b * kTriEBytes), 64 * 256, 1024);
+    int stage = 0;
+    uint32_t sphase = 0, aphase = 0, tcount = 0;
+    uint32_t ecnt[2] = {0u, 0u};
+    bool pend[2] = {false, false};
+    // column sums of the E tile in buffer b: K = 128 rows of E, 16 per step (2048 B apart in the MN-major tile)
+    auto issue_colsum = [&](int b) {
+      ptx::mbar_wait(&e_full[b], ecnt[b] & 1u);
+      ptx::mbar_wait(&d_empty[b], (ecnt[b] & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t boff = (uint32_t)(((k >> 2) * 2048 + (k & 3) * 32) >> 4);
+          ptx::umma_ss(tmem_base + kTriColD2 + (uint32_t)b * 16u, e_desc[b] + (uint32_t)(k * 2048 >> 4), ones_desc + boff, idesc_c,
+                       k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&e_empty[b]);
+        ptx::umma_commit(&d_full[b]);
+      }
+      __syncwarp();
+      ++ecnt[b];
+    };
+    for (int item = blockIdx.x; item < n_items; item += G) {
+      int rb, cc, lo, hi;
+      tri_item(item, sch, G, rb, cc, lo, hi);
+      if (lo >= hi) continue;
+      ptx::mbar_wait(a_full, aphase);
+      aphase ^= 1;
+      ptx::tc_fence_after();
+      for (int ct = lo; ct < hi; ++ct, ++tcount) {
+        const int b = (int)(tcount & 1u);
+        ptx::mbar_wait(&tempty[b], ((tcount >> 1) & 1u) ^ 1u);
+        ptx::mbar_wait(&full[stage], sphase);
+        ptx::tc_fence_after();
+        const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + (size_t)stage * kFwdPanelBytes * kMaxPanels), 16, 1024);
+        const uint32_t d_tmem = tmem_base + kTriColS + (uint32_t)b * kBN;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < NP * 4; ++kk) {
+            const uint32_t off16 = (uint32_t)(((kk >> 2) * kFwdPanelBytes + (kk & 3) * 32) >> 4);
+            ptx::umma_ts(d_tmem, tmem_base + (uint32_t)kk * 8u, bdesc + off16, idesc_s, kk > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);
+          ptx::umma_commit(&tfull[b]);
+        }
+        __syncwarp();
+        // the previous tile on this buffer pair (two tiles back) has had a whole S MMA of time to finish its E tile
+        if (pend[b]) issue_colsum(b);
+        pend[b] = (ct != rb);
+        if (++stage == kTriStages) { stage = 0; sphase ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(a_empty);
+      __syncwarp();
+    }
+    for (int b = 0; b < 2; ++b)
+      if (pend[b]) issue_colsum(b);
+  } else {  // ---------------- softmax warpgroups ----------------
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* myE = sE + (size_t)wg * kTriEBytes;
+    float* mycol = partial + (size_t)(2 * sch.nchunks + 2 * blockIdx.x + wg) * rows_padded;  // column-sum slot of (CTA, warpgroup)
+    uint32_t tcount = 0, aphase = 0, ecnt = 0, dcnt = 0;
+    int pend_cb = -1;
+    auto drain = [&]() {  // column sums of my previous off-diagonal tile: lane j of D2 holds sum_i E[i][j]
+      ptx::mbar_wait(&d_full[wg], dcnt & 1u);
+      ptx::tc_fence_after();
+      uint32_t r[32];
+      ptx::tmem_ld32(lane_base + kTriColD2 + (uint32_t)wg * 16u, r);
+      ptx::tmem_ld_wait();
+      mycol[(size_t)pend_cb * kBN + lrow] += __uint_as_float(r[0]);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&d_empty[wg]);
+      ++dcnt;
+      pend_cb = -1;
+    };
+    for (int item = blockIdx.x; item < n_items; item += G) {
+      int rb, cc, lo, hi;
+      tri_item(item, sch, G, rb, cc, lo, hi);
+      if (lo >= hi) continue;
+      if (wg == 0) {
+        ptx::mbar_wait(a_empty, aphase ^ 1);
+        aphase ^= 1;
+        ptx::tc_fence_after();
+        stage_rows_to_tmem(z, rows, D, rb * kBM + lrow, lane_base);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full);
+      }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int ct = lo; ct < hi; ++ct, ++tcount) {
+        if ((int)(tcount & 1u) != wg) continue;
+        if (pend_cb >= 0) drain();
+        const bool diag = (ct == rb);
+        ptx::mbar_wait(&tfull[wg], (tcount >> 1) & 1u);
+        ptx::tc_fence_after();
+        if (!diag) ptx::mbar_wait(&e_empty[wg], (ecnt & 1u) ^ 1u);   // the column-sum MMA of my previous E tile has retired
+        const uint32_t taddr = lane_base + kTriColS + (uint32_t)wg * kBN;
+        uint32_t ra[32], rb_[32];
+        auto consume = [&](uint32_t (&r)[32], int c) {
+          if (diag) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j == lrow) r[j] = 0xff800000u;  // -inf -> ex2 = 0
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float e0 = ex2(__uint_as_float(r[j])), e1 = ex2(__uint_as_float(r[j + 1]));
+            const float e2 = ex2(__uint_as_float(r[j + 2])), e3 = ex2(__uint_as_float(r[j + 3]));
+            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+            r[j >> 1] = pack2(e0, e1);         // bf16 pairs reuse the low half of r[] (index j/2 <= j: already consumed)
+            r[(j >> 1) + 1] = pack2(e2, e3);
+          }
+          if (!diag) {
+            // row lrow of the E tile, columns [32c, 32c+32): 64-column panel c>>1, 16-byte chunks (c&1)*4 .. +3, XOR-swizzled by row
+            uint8_t* rowp = myE + (size_t)(c >> 1) * (64 * 256) + (size_t)lrow * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = ((c & 1) * 4 + q) ^ (lrow & 7);
+              *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            }
+          }
+        };
+        ptx::tmem_ld32(taddr, ra);
+        ptx::tmem_ld32(taddr + 32, rb_);
+        ptx::tmem_ld_wait();
+        consume(ra, 0);
+        ptx::tmem_ld32(taddr + 64, ra);
+        consume(rb_, 1);
+        ptx::tmem_ld32(taddr + 96, rb_);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[wg]);
+        consume(ra, 2);
+        consume(rb_, 3);
+        if (!diag) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&e_full[wg]);
+          ++ecnt;
+          pend_cb = ct;
+        }
+      }
+      const int row = rb * kBM + lrow;
+      if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s0 + s1) + (s2 + s3);
+    }
+    if (pend_cb >= 0) drain();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // R_u, 1/R_u, ln R_u and the positive-pair logits; fixed-order block partials.
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
                                                                     int row_begin, int rows, int rows_pad_end, int N, int D, float npad,
@@ -847,7 +1109,19 @@ static bool rows_range_ok(int64_t rows, int64_t b, int64_t e) {
   return b >= 0 && b < e && e <= rows && b % kBM == 0 && (e % kBM == 0 || e == rows);
 }
 
-// partial row sums [2 * nchunks][padded rows] + per-CTA loss partials; nchunks depends on how many row blocks the launch owns
+// BMKG_INFONCE_FWD=tri selects the upper-triangle forward for full-range launches (read once per process)
+static bool fwd_tri_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BMKG_INFONCE_FWD");
+    v = (e && e[0] == 't') ? 1 : 0;
+  }
+  return v == 1;
+}
+static int64_t fwd_slots(const Schedule& s, bool tri) { return 2 * (int64_t)s.nchunks + (tri ? 2 * kNumSMs : 0); }
+
+// partial row sums [2 * nchunks][padded rows] (+ [2 * SMs][padded rows] column-sum slots for the triangular forward) + per-CTA
+// loss partials; nchunks depends on how many row blocks the launch owns
 size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int D, int64_t row_begin, int64_t row_end) {
   (void)D;
   const int64_t rows = 2 * N;
@@ -855,7 +1129,7 @@ size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int D, int64_t row_begin, in
   Schedule s = make_schedule(rows, row_begin, row_end);
   const int64_t rp = bmkg_infonce_padded_rows(N);
   WsCarver c(nullptr);
-  c.take<float>((size_t)2 * s.nchunks * rp);
+  c.take<float>((size_t)fwd_slots(s, fwd_tri_enabled() && row_begin == 0 && row_end == rows) * rp);
   c.take<float>((size_t)ceil_div(rp, 256));
   return c.used();
 }
@@ -874,8 +1148,9 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
   BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes_rows(N, D, row_begin, row_end), BMKG_ERR_WORKSPACE);
   const int64_t rp = bmkg_infonce_padded_rows(N);
   Schedule s = make_schedule(rows, row_begin, row_end);
+  const bool tri = fwd_tri_enabled() && row_begin == 0 && row_end == rows;
   WsCarver c(ws);
-  float* partial = c.take<float>((size_t)2 * s.nchunks * rp);
+  float* partial = c.take<float>((size_t)fwd_slots(s, tri) * rp);
   const int nb = (int)ceil_div(rp, 256);
   float* block_part = c.take<float>(nb);
 
@@ -885,6 +1160,30 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
   const int n_items = s.nrb * s.nchunks;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
+  int nslots = 2 * s.nchunks;
+  if (tri) {
+    // triangular forward: row-sum slots of skipped (row block, chunk) items and the per-(CTA, warpgroup) column-sum slots start at 0
+    nslots = 2 * s.nchunks + 2 * grid;
+    if (cudaMemsetAsync(partial, 0, (size_t)nslots * rp * sizeof(float), st) != cudaSuccess) return BMKG_ERR_LAUNCH;
+#define BMKG_LAUNCH_TRI(NP_)                                                                                                      \
+  {                                                                                                                               \
+    static bool attr_set = false;                                                                                                 \
+    if (!attr_set) {                                                                                                              \
+      if (cudaFuncSetAttribute(infonce_fwd_tri_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemBytes) !=   \
+          cudaSuccess)                                                                                                            \
+        return BMKG_ERR_LAUNCH;                                                                                                   \
+      attr_set = true;                                                                                                            \
+    }                                                                                                                             \
+    infonce_fwd_tri_kernel<NP_><<<grid, kThreads, kTriSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, partial);                \
+  }
+    switch (D / kPanelElems) {
+      case 1: BMKG_LAUNCH_TRI(1) break;
+      case 2: BMKG_LAUNCH_TRI(2) break;
+      case 3: BMKG_LAUNCH_TRI(3) break;
+      default: BMKG_LAUNCH_TRI(4) break;
+    }
+#undef BMKG_LAUNCH_TRI
+  } else {
 #define BMKG_LAUNCH_FWD(NP_)                                                                                                      \
   {                                                                                                                               \
     static bool attr_set = false;                                                                                                 \
@@ -903,12 +1202,13 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
     default: BMKG_LAUNCH_FWD(4) break;
   }
 #undef BMKG_LAUNCH_FWD
+  }
   BMKG_CHECK_LAUNCH();
   const float npad = (float)(s.ntiles * kBN - rows);
   // rows of this launch: [row_begin, row_end); the zero padding of inv_r beyond 2N belongs to the launch that owns the last row
   const int64_t pad_end = (row_end == rows) ? rp : row_end;
   const int nbr = (int)ceil_div(pad_end - row_begin, 256);
-  infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, 2 * s.nchunks, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
+  infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, nslots, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
                                                     D, npad, static_cast<const __nv_bfloat16*>(z_bf16), inv_r, block_part);
   infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nbr, 1.0f / (2.0f * (float)N), loss);
   BMKG_CHECK_LAUNCH();

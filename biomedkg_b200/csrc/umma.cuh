@@ -129,6 +129,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------ descriptors --------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.
 //   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
