@@ -141,7 +141,13 @@ def test_infonce_cluster_closed_form_large_n(n):
     assert abs(inv_tau * tau - 1.0) < 2e-3                                     # inside the 1e-3-relative loss budget
     R = (nc - 1.0) * math.exp(inv_tau) + (2.0 * n - nc)
     ref = float((torch.log(R) * nc).sum() / (2.0 * n) - inv_tau)
-    assert abs(float(loss) - ref) <= 2e-5 * abs(ref), (float(loss), ref)
+    # The experimental triangular forward (BMKG_INFONCE_FWD=tri) sums bf16-rounded E in the column part of R.  Here every
+    # same-cluster entry is the SAME number (2^7.2227 = 149.36 -> 149 in bf16, -0.24 %), so the rounding does not average
+    # out as it does for generic inputs: up to ~1.2e-3 in ln R, ~2e-4 relative in the loss - inside the stated 1e-3 budget.
+    import os
+
+    tight = 4e-4 if os.environ.get("BMKG_INFONCE_FWD", "").startswith("t") else 2e-5
+    assert abs(float(loss) - ref) <= tight * abs(ref), (float(loss), ref)
     R = (nc - 1.0) * math.exp(1.0 / tau) + (2.0 * n - nc)                      # exact-arithmetic value: the stated tolerance
     exact = float((torch.log(R) * nc).sum() / (2.0 * n) - 1.0 / tau)
     assert abs(float(loss) - exact) <= 1e-3 * abs(exact)
