@@ -104,7 +104,12 @@ def test_row_sharded_entry_points_compose(n, d, splits):
         loss += l
         inv += i
     assert abs(float(loss) - float(full_loss)) < 1e-6 * abs(float(full_loss))
-    assert torch.allclose(inv, full_inv, rtol=2e-6, atol=0)      # column-chunk grouping of the partial sums depends on the range
+    # column-chunk grouping of the partial sums depends on the range; with the experimental triangular forward
+    # (BMKG_INFONCE_FWD=tri, full-range launches only) the full launch also carries bf16-rounded column sums
+    import os
+
+    tri = os.environ.get("BMKG_INFONCE_FWD", "").startswith("t")
+    assert torch.allclose(inv, full_inv, rtol=1e-3 if tri else 2e-6, atol=0)
     dz = torch.zeros_like(full_dz)
     for r0, r1 in zip(splits, splits[1:]):
         dz += impl.bwd_rows(z, inv, gs, n, r0, r1)
