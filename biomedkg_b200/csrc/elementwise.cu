@@ -224,26 +224,89 @@ __global__ void __launch_bounds__(kEwThreads) mask_cast_bwd_kernel(const __nv_bf
   }
 }
 
-// one warp per row: z = bf16( h / max(|h|, eps) * scale ), inv_norm = 1 / max(|h|, eps)
-__global__ void __launch_bounds__(256) l2norm_scale_kernel(const float* __restrict__ h, int64_t N, int D, float scale,
-                                                           __nv_bfloat16* __restrict__ z, float* __restrict__ inv_norm) {
+// out = bf16(x - m): the deviation operand of a centred GEMM  x W^T = (x - 1 m^T) W^T + 1 (W m)^T  (projector, model/gcl.py:49-51)
+__global__ void __launch_bounds__(kEwThreads) center_cast_kernel(const float* __restrict__ x, const float* __restrict__ m, int64_t n4,
+                                                                 int C4, __nv_bfloat16* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 c = reinterpret_cast<const float4*>(m)[i % C4];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack2(v.x - c.x, v.y - c.y), pack2(v.z - c.z, v.w - c.w));
+  }
+}
+
+// Centred InfoNCE operand (numerics: DESIGN.md "Centred bf16 operands").  At initialisation, and whenever the encoder
+// over-smooths, the normalised rows z_u are nearly identical; the InfoNCE gradient then lives in deviations of relative
+// size 1e-3 that a bf16 z (2^-9) cannot carry.  Z is therefore stored as a common fp32 vector mu plus bf16 deviations
+// d_u = z_u - mu, and the kernels use  z_u . z_v = d_u . d_v + a_u + a_v + |mu|^2  with a_u = mu . d_u in fp32.
+//
+// pass 1: inv_norm[u] = 1 / max(|h_u|, eps) and per-CTA column partial sums of h_u * inv_norm[u]
+__global__ void __launch_bounds__(256) l2norm_colsum_kernel(const float* __restrict__ h, int64_t N, int D, int rows_per_cta,
+                                                            float* __restrict__ inv_norm, float* __restrict__ partial /*[grid, D]*/) {
+  extern __shared__ float red[];  // [8][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  float acc[8][4];  // D <= 1024: lane owns columns lane*4 + 128*k
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+  for (int64_t row = r0 + warp; row < r1; row += 8) {
+    const float* hp = h + row * D;
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane * 4 + 128 * k;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < D) v[k] = *reinterpret_cast<const float4*>(hp + c);
+      ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[row] = inv;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k][0] = fmaf(v[k].x, inv, acc[k][0]);
+      acc[k][1] = fmaf(v[k].y, inv, acc[k][1]);
+      acc[k][2] = fmaf(v[k].z, inv, acc[k][2]);
+      acc[k][3] = fmaf(v[k].w, inv, acc[k][3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < D) *reinterpret_cast<float4*>(red + warp * D + c) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w * D + c];   // fixed warp order: deterministic
+    partial[(int64_t)blockIdx.x * D + c] = s;
+  }
+}
+
+// pass 2: d_u = bf16(h_u * inv_norm[u] * scale - mu), a_u = mu . d_u (of the ROUNDED deviation, fp32)
+__global__ void __launch_bounds__(256) center_scale_kernel(const float* __restrict__ h, const float* __restrict__ inv_norm,
+                                                           const float* __restrict__ mu, int64_t N, int D, float scale,
+                                                           __nv_bfloat16* __restrict__ z, float* __restrict__ a) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
+  const float s = inv_norm[row] * scale;
   const float* hp = h + row * D;
-  float ss = 0.f;
+  float dot = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(hp + c);
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    const float4 m = *reinterpret_cast<const float4*>(mu + c);
+    const uint32_t lo = pack2(fmaf(v.x, s, -m.x), fmaf(v.y, s, -m.y));
+    const uint32_t hi = pack2(fmaf(v.z, s, -m.z), fmaf(v.w, s, -m.w));
+    *reinterpret_cast<uint2*>(z + row * D + c) = make_uint2(lo, hi);
+    dot = fmaf(m.x, __uint_as_float(lo << 16), dot);
+    dot = fmaf(m.y, __uint_as_float(lo & 0xffff0000u), dot);
+    dot = fmaf(m.z, __uint_as_float(hi << 16), dot);
+    dot = fmaf(m.w, __uint_as_float(hi & 0xffff0000u), dot);
   }
-  ss = warp_sum(ss);
-  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-  if (lane == 0) inv_norm[row] = inv;
-  const float s = inv * scale;
-  for (int c = lane * 4; c < D; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(hp + c);
-    *reinterpret_cast<uint2*>(z + row * D + c) = make_uint2(pack2(v.x * s, v.y * s), pack2(v.z * s, v.w * s));
-  }
+  dot = warp_sum(dot);
+  if (lane == 0) a[row] = dot;
 }
 
 // dh = scale * inv * (dz - u (u . dz)),  u = h * inv   (straight-through the bf16 rounding)
@@ -386,11 +449,34 @@ int bmkg_colsum(const float* z, const float* row_weight, int64_t N, int C, float
   return BMKG_OK;
 }
 
-int bmkg_l2norm_scale(const float* h, int64_t N, int D, float scale, void* z_bf16, float* inv_norm, void* stream) {
-  BMKG_REQUIRE(h && z_bf16 && inv_norm && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
-  BMKG_REQUIRE(aligned16(h) && aligned16(z_bf16), BMKG_ERR_MISALIGNED);
-  l2norm_scale_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      h, N, D, scale, static_cast<__nv_bfloat16*>(z_bf16), inv_norm);
+int bmkg_center_cast(const float* x, const float* m, int64_t N, int C, void* out_bf16, void* stream) {
+  BMKG_REQUIRE(x && m && out_bf16 && N > 0 && C > 0 && C % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(x) && aligned16(m) && aligned16(out_bf16), BMKG_ERR_MISALIGNED);
+  center_cast_kernel<<<ew_grid(N * (C / 4)), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, m, N * (C / 4), C / 4, static_cast<__nv_bfloat16*>(out_bf16));
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_l2norm_colsum(const float* h, int64_t N, int D, float* inv_norm, float* colsum, void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(h && inv_norm && colsum && N > 0 && D > 0 && D % 4 == 0 && D <= 1024, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_colsum_workspace_bytes(N, D), BMKG_ERR_WORKSPACE);
+  BMKG_REQUIRE(aligned16(h), BMKG_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nb = colsum_ctas(N);
+  const int rows_per_cta = (int)ceil_div(N, nb);
+  l2norm_colsum_kernel<<<nb, 256, 8 * D * sizeof(float), st>>>(h, N, D, rows_per_cta, inv_norm, static_cast<float*>(ws));
+  colsum_finish_kernel<<<(unsigned)ceil_div(D, 32), kFinishThreads, 0, st>>>(static_cast<const float*>(ws), nb, D, D, colsum);
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_center_scale(const float* h, const float* inv_norm, const float* mu, int64_t N, int D, float scale, void* z_bf16,
+                      float* a, void* stream) {
+  BMKG_REQUIRE(h && inv_norm && mu && z_bf16 && a && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(h) && aligned16(z_bf16) && aligned16(mu), BMKG_ERR_MISALIGNED);
+  center_scale_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h, inv_norm, mu, N, D, scale, static_cast<__nv_bfloat16*>(z_bf16), a);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

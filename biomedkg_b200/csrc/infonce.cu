@@ -13,6 +13,16 @@
 //      loss = (1/2N) [ sum_u ln R_u - 2 ln2 sum_i z_i . z_{N+i} ].
 // |logit| <= 1/tau so a fixed shift replaces the online max: no rescale pass.
 //
+// Centred operand.  Z is stored as a common fp32 vector mu plus bf16 deviations d_u = z_u - mu (bmkg_center_scale), because
+// near-collapsed embeddings (initialisation, over-smoothing) differ only at the 1e-3 level, below bf16 resolution:
+//      z_u . z_v = d_u . d_v + a_u + a_v + |mu|^2,     a_u = mu . d_u  (fp32)
+// The tensor core contracts the deviations; a_v is added per column before ex2 and the row factor 2^(a_u + |mu|^2) is
+// taken out of the sum:  R_u = 2^(a_u + |mu|^2) R'_u,  R'_u = sum_{v != u} 2^(d_u . d_v + a_v).  |mu|^2 cancels in the loss:
+//      loss = (1/2N) [ sum_u ln R'_u - ln2 sum_u a_u - 2 ln2 sum_i d_i . d_{N+i} ]
+// and with q_u = 1/R'_u, w_u = 2^(a_u) the backward weights are  P_uv = 2^(d_u . d_v) (q_u w_v + q_v w_u)  (symmetric),
+//      dZ_u = (ln2/2N) [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ].
+// bf16 P only ever multiplies deviations; the common part rides on fp32 row sums.  mu = 0 gives the plain formulation.
+//
 // Forward: persistent CTAs; each work item is a 128-row block of Z (A operand, staged once into TMEM - the TS form
 // keeps it off the shared-memory read path) against a chunk of 128-row column tiles of Z (B operand) streamed through a
 // 3-stage TMA + mbarrier ring; tcgen05.mma (M=128,N=128,K=16, bf16 -> fp32) writes S tiles into a 3-deep ring of TMEM
@@ -35,17 +45,14 @@ namespace nce {
 
 constexpr int kBM = 128;             // rows of Z per CTA work item (UMMA M)
 constexpr int kBN = 128;             // forward: rows of Z per streamed column tile (UMMA N)
-constexpr int kBNb = 64;             // backward: column-tile rows (UMMA N of MMA1, K of MMA2)
 constexpr int kPanelElems = 64;      // 64 bf16 = 128 B = one swizzle row
 constexpr int kMaxPanels = 4;        // D <= 256
 constexpr int kThreads = 320;        // warp0 TMA, warp1 MMA, warps 2-9 softmax (2 warpgroups)
 constexpr int kTmemCols = 512;
-// forward: 3 stages of (128 rows x 512 B); backward: 5 stages of (64 rows x 512 B).  The stationary row block (A) lives in
-// TMEM, not smem: the SS form would re-read it from shared memory for every MMA and the kernels are smem-bandwidth bound.
+// forward: 3 stages of (128 rows x 512 B).  The stationary row block (A) lives in TMEM, not smem: the SS form would re-read
+// it from shared memory for every MMA and the kernel is smem-bandwidth bound.
 constexpr int kFwdStages = 3, kFwdAcc = 3, kFwdPanelBytes = kBN * 128;
-constexpr int kBwdStages = 5, kBwdPanelBytes = kBNb * 128;
 constexpr size_t kFwdSmemBytes = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages + 256;
-constexpr size_t kBwdSmemBytes = 1024 + (size_t)kBwdPanelBytes * kMaxPanels * kBwdStages + 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -82,7 +89,8 @@ __device__ __forceinline__ void stage_rows_to_tmem(const __nv_bfloat16* __restri
 template <int NP>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
-                   const __nv_bfloat16* __restrict__ z, float* __restrict__ partial) {
+                   const __nv_bfloat16* __restrict__ z, const float* __restrict__ a /*[rows_padded], 0 beyond rows*/,
+                   float* __restrict__ partial) {
   constexpr int D = NP * kPanelElems;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -201,6 +209,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         const bool diag = (ct == rb);
         // 128 columns in 4 chunks of 32, loads issued two chunks ahead of the exp/sum so TMEM latency is hidden
         uint32_t ra[32], rb_[32];
+        const float4* avp = reinterpret_cast<const float4*>(a + (size_t)ct * kBN);   // a_v of this tile's columns (lane-uniform)
         auto consume = [&](uint32_t (&r)[32], int c) {
           if (diag) {
 #pragma unroll
@@ -209,10 +218,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            s0 += ex2(__uint_as_float(r[j]));
-            s1 += ex2(__uint_as_float(r[j + 1]));
-            s2 += ex2(__uint_as_float(r[j + 2]));
-            s3 += ex2(__uint_as_float(r[j + 3]));
+            const float4 av = __ldg(avp + c * 8 + (j >> 2));
+            s0 += ex2(__uint_as_float(r[j]) + av.x);
+            s1 += ex2(__uint_as_float(r[j + 1]) + av.y);
+            s2 += ex2(__uint_as_float(r[j + 2]) + av.z);
+            s3 += ex2(__uint_as_float(r[j + 3]) + av.w);
           }
         };
         ptx::tmem_ld32(taddr, ra);
@@ -239,285 +249,27 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// ----------------------------------------------------------------------------
-// forward on the upper triangle of the Gram matrix  (BMKG_INFONCE_FWD=tri; full-range launches only)
-// ----------------------------------------------------------------------------
-// E = 2^S is symmetric, so only tiles (rb, cb) with cb >= rb are computed: an off-diagonal tile adds its ROW sums to the
-// rows of block rb (registers, as in the kernel above) and its COLUMN sums to the rows of block cb.  The column sums come
-// from the tensor core with the column index on the TMEM lanes: the softmax warpgroup stores E (bf16) in shared memory in
-// the MN-major 128-byte-swizzle layout (thread i writes its own row), and one small MMA
-//     D2[128 x 16] = E^T[M = j, K = i] * Ones[K = i, N = 16]              (A = E buffer read MN-major, B = constant ones)
-// leaves column sum j in lane j (0.5 MFLOP against 8.4 for the S tile); thread j adds it to a slot private to
-// (CTA, warpgroup) that the finaliser sums in fixed order (deterministic, no atomics).  8 N^2 D -> ~4.3 N^2 D executed and
-// half the ex2 work.  TMEM: [0,128) stationary rows, [128,384) S ring (2), [384,400) / [400,416) D2 of warpgroup 0 / 1.
-// Tile t of a CTA (running count) uses S buffer, E buffer and D2 number t & 1 and is handled by warpgroup t & 1.
-constexpr int kTriStages = 2;
-constexpr int kTriEBytes = kBM * kBN * 2;    // one E tile, bf16
-constexpr int kTriOnesBytes = 16 * 128 * 2;  // B operand of the column-sum MMA: 16 x 128 bf16 ones (K-major, two 64-wide panels)
-constexpr uint32_t kTriColS = 128, kTriColD2 = 384;
-constexpr size_t kTriSmemBytes =
-    1024 + (size_t)kFwdPanelBytes * kMaxPanels * kTriStages + 2 * (size_t)kTriEBytes + kTriOnesBytes + 256;
-
-// work item -> (row block, column chunk, tile range).  Row blocks are dealt to the CTAs in snake order per round so that
-// long (small rb) and short (large rb) strips of the triangle mix on every CTA.  Every role calls this with the same item.
-__device__ __forceinline__ void tri_item(int item, const Schedule& sch, int G, int& rb, int& cc, int& lo, int& hi) {
-  cc = item / sch.nrb;
-  const int r = item % sch.nrb;
-  const int round = r / G;
-  int pos = r % G;
-  if (round < sch.nrb / G && (round & 1)) pos = G - 1 - pos;
-  rb = sch.rb0 + round * G + pos;
-  const int t0 = cc * sch.tiles_per_chunk;
-  hi = min(sch.ntiles, t0 + sch.tiles_per_chunk);
-  lo = max(t0, rb);
-}
-
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-infonce_fwd_tri_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
-                       const __nv_bfloat16* __restrict__ z, float* __restrict__ partial) {
-  constexpr int D = NP * kPanelElems;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
-  uint8_t* sB = smem;
-  uint8_t* sE = sB + (size_t)kFwdPanelBytes * kMaxPanels * kTriStages;  // two E tiles, 1024-byte aligned
-  uint8_t* sOnes = sE + 2 * (size_t)kTriEBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kTriOnesBytes);
-  uint64_t* full = bars;                    // [kTriStages]
-  uint64_t* empty = full + kTriStages;      // [kTriStages]
-  uint64_t* a_full = empty + kTriStages;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* tfull = a_empty + 1;            // [2] S tile ready
-  uint64_t* tempty = tfull + 2;             // [2] S tile drained to registers (4 warp arrivals)
-  uint64_t* e_full = tempty + 2;            // [2] E tile written by the warpgroup (4 warp arrivals)
-  uint64_t* e_empty = e_full + 2;           // [2] column-sum MMA has read the E tile
-  uint64_t* d_full = e_empty + 2;           // [2] column sums in TMEM
-  uint64_t* d_empty = d_full + 2;           // [2] column sums read back (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int G = gridDim.x;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTriStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    ptx::mbar_init(a_full, 4);
-    ptx::mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4);
-      ptx::mbar_init(&e_full[b], 4); ptx::mbar_init(&e_empty[b], 1);
-      ptx::mbar_init(&d_full[b], 1); ptx::mbar_init(&d_empty[b], 4);
-    }
-    ptx::fence_barrier_init();
-    ptx::prefetch_tensormap(&tmap);
-  }
-  for (int i = threadIdx.x; i < kTriOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
-  ptx::fence_proxy_async_smem();
-  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int n_items = sch.nrb * sch.nchunks;
-  const uint32_t tile_bytes = (uint32_t)NP * kFwdPanelBytes;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      int stage = 0;
-      uint32_t sphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += G) {
-        int rb, cc, lo, hi;
-        tri_item(item, sch, G, rb, cc, lo, hi);
-        for (int ct = lo; ct < hi; ++ct) {
-          ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
-          uint8_t* dst = sB + (size_t)stage * kFwdPanelBytes * kMaxPanels;
-          for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kFwdPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
-          if (++stage == kTriStages) { stage = 0; sphase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {  // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);   // S = A(tmem) B^T
-    constexpr uint32_t idesc_c = ptx::idesc_bf16_f32(kBM, 16, 1, 0);    // D2 = E^T(smem, MN-major) Ones
-    const uint64_t ones_desc = ptx::smem_desc_sw128(ptx::smem_u32(sOnes), 16, 1024);
-    uint64_t e_desc[2];
-    for (int b = 0; b < 2; ++b) e_desc[b] = ptx::smem_desc_sw128(ptx::smem_u32(sE + (size_t)b * kTriEBytes), 64 * 256, 1024);
-    int stage = 0;
-    uint32_t sphase = 0, aphase = 0, tcount = 0;
-    uint32_t ecnt[2] = {0u, 0u};
-    bool pend[2] = {false, false};
-    // column sums of the E tile in buffer b: K = 128 rows of E, 16 per step (2048 B apart in the MN-major tile)
-    auto issue_colsum = [&](int b) {
-      ptx::mbar_wait(&e_full[b], ecnt[b] & 1u);
-      ptx::mbar_wait(&d_empty[b], (ecnt[b] & 1u) ^ 1u);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t boff = (uint32_t)(((k >> 2) * 2048 + (k & 3) * 32) >> 4);
-          ptx::umma_ss(tmem_base + kTriColD2 + (uint32_t)b * 16u, e_desc[b] + (uint32_t)(k * 2048 >> 4), ones_desc + boff, idesc_c,
-                       k > 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(&e_empty[b]);
-        ptx::umma_commit(&d_full[b]);
-      }
-      __syncwarp();
-      ++ecnt[b];
-    };
-    for (int item = blockIdx.x; item < n_items; item += G) {
-      int rb, cc, lo, hi;
-      tri_item(item, sch, G, rb, cc, lo, hi);
-      if (lo >= hi) continue;
-      ptx::mbar_wait(a_full, aphase);
-      aphase ^= 1;
-      ptx::tc_fence_after();
-      for (int ct = lo; ct < hi; ++ct, ++tcount) {
-        const int b = (int)(tcount & 1u);
-        ptx::mbar_wait(&tempty[b], ((tcount >> 1) & 1u) ^ 1u);
-        ptx::mbar_wait(&full[stage], sphase);
-        ptx::tc_fence_after();
-        const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + (size_t)stage * kFwdPanelBytes * kMaxPanels), 16, 1024);
-        const uint32_t d_tmem = tmem_base + kTriColS + (uint32_t)b * kBN;
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < NP * 4; ++kk) {
-            const uint32_t off16 = (uint32_t)(((kk >> 2) * kFwdPanelBytes + (kk & 3) * 32) >> 4);
-            ptx::umma_ts(d_tmem, tmem_base + (uint32_t)kk * 8u, bdesc + off16, idesc_s, kk > 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(&empty[stage]);
-          ptx::umma_commit(&tfull[b]);
-        }
-        __syncwarp();
-        // the previous tile on this buffer pair (two tiles back) has had a whole S MMA of time to finish its E tile
-        if (pend[b]) issue_colsum(b);
-        pend[b] = (ct != rb);
-        if (++stage == kTriStages) { stage = 0; sphase ^= 1; }
-      }
-      if (ptx::elect_one()) ptx::umma_commit(a_empty);
-      __syncwarp();
-    }
-    for (int b = 0; b < 2; ++b)
-      if (pend[b]) issue_colsum(b);
-  } else {  // ---------------- softmax warpgroups ----------------
-    const int wg = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* myE = sE + (size_t)wg * kTriEBytes;
-    float* mycol = partial + (size_t)(2 * sch.nchunks + 2 * blockIdx.x + wg) * rows_padded;  // column-sum slot of (CTA, warpgroup)
-    uint32_t tcount = 0, aphase = 0, ecnt = 0, dcnt = 0;
-    int pend_cb = -1;
-    auto drain = [&]() {  // column sums of my previous off-diagonal tile: lane j of D2 holds sum_i E[i][j]
-      ptx::mbar_wait(&d_full[wg], dcnt & 1u);
-      ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld32(lane_base + kTriColD2 + (uint32_t)wg * 16u, r);
-      ptx::tmem_ld_wait();
-      mycol[(size_t)pend_cb * kBN + lrow] += __uint_as_float(r[0]);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&d_empty[wg]);
-      ++dcnt;
-      pend_cb = -1;
-    };
-    for (int item = blockIdx.x; item < n_items; item += G) {
-      int rb, cc, lo, hi;
-      tri_item(item, sch, G, rb, cc, lo, hi);
-      if (lo >= hi) continue;
-      if (wg == 0) {
-        ptx::mbar_wait(a_empty, aphase ^ 1);
-        aphase ^= 1;
-        ptx::tc_fence_after();
-        stage_rows_to_tmem(z, rows, D, rb * kBM + lrow, lane_base);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full);
-      }
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int ct = lo; ct < hi; ++ct, ++tcount) {
-        if ((int)(tcount & 1u) != wg) continue;
-        if (pend_cb >= 0) drain();
-        const bool diag = (ct == rb);
-        ptx::mbar_wait(&tfull[wg], (tcount >> 1) & 1u);
-        ptx::tc_fence_after();
-        if (!diag) ptx::mbar_wait(&e_empty[wg], (ecnt & 1u) ^ 1u);   // the column-sum MMA of my previous E tile has retired
-        const uint32_t taddr = lane_base + kTriColS + (uint32_t)wg * kBN;
-        uint32_t ra[32], rb_[32];
-        auto consume = [&](uint32_t (&r)[32], int c) {
-          if (diag) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j == lrow) r[j] = 0xff800000u;  // -inf -> ex2 = 0
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float e0 = ex2(__uint_as_float(r[j])), e1 = ex2(__uint_as_float(r[j + 1]));
-            const float e2 = ex2(__uint_as_float(r[j + 2])), e3 = ex2(__uint_as_float(r[j + 3]));
-            s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-            r[j >> 1] = pack2(e0, e1);         // bf16 pairs reuse the low half of r[] (index j/2 <= j: already consumed)
-            r[(j >> 1) + 1] = pack2(e2, e3);
-          }
-          if (!diag) {
-            // row lrow of the E tile, columns [32c, 32c+32): 64-column panel c>>1, 16-byte chunks (c&1)*4 .. +3, XOR-swizzled by row
-            uint8_t* rowp = myE + (size_t)(c >> 1) * (64 * 256) + (size_t)lrow * 128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int chunk = ((c & 1) * 4 + q) ^ (lrow & 7);
-              *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-            }
-          }
-        };
-        ptx::tmem_ld32(taddr, ra);
-        ptx::tmem_ld32(taddr + 32, rb_);
-        ptx::tmem_ld_wait();
-        consume(ra, 0);
-        ptx::tmem_ld32(taddr + 64, ra);
-        consume(rb_, 1);
-        ptx::tmem_ld32(taddr + 96, rb_);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty[wg]);
-        consume(ra, 2);
-        consume(rb_, 3);
-        if (!diag) {
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&e_full[wg]);
-          ++ecnt;
-          pend_cb = ct;
-        }
-      }
-      const int row = rb * kBM + lrow;
-      if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s0 + s1) + (s2 + s3);
-    }
-    if (pend_cb >= 0) drain();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
-}
-
-// R_u, 1/R_u, ln R_u and the positive-pair logits; fixed-order block partials.
+// R'_u, q_u = 1/R'_u, w_u = 2^(a_u), and the loss terms ln R'_u - ln2 a_u - 2 ln2 d_i . d_{N+i}; fixed-order block partials.
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
-                                                                    int row_begin, int rows, int rows_pad_end, int N, int D, float npad,
-                                                                    const __nv_bfloat16* __restrict__ z,
-                                                                    float* __restrict__ inv_r, float* __restrict__ block_part) {
+                                                                    int row_begin, int row_end, int rows_pad_end, int N, int B, int D, float npad,
+                                                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ a,
+                                                                    float2* __restrict__ qw, float* __restrict__ block_part) {
   __shared__ float red[8];
-  const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, rows) are this launch's
+  const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, row_end) are this launch's
   float term = 0.f;
-  if (u < rows) {
+  // block-interleaved stacked layout (see bmkg_b200.h): rows [2kB, 2kB + B) = view 1 of nodes [kB, kB + B), the next B rows
+  // view 2 of the same nodes; rows of nodes >= N are zero padding
+  const int blk = u / B;
+  if (u < row_end && (blk >> 1) * B + (u - blk * B) < N) {
     float R = 0.f;
     for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
-    R -= npad;
-    inv_r[u] = 1.0f / R;
-    term = logf(R);
-    if (u < N) {
+    R -= npad;                      // zero-filled out-of-range columns have a_v = 0 and contributed exactly 1.0 each
+    const float au = a[u];
+    qw[u] = make_float2(1.0f / R, exp2f(au));
+    term = logf(R) - 0.6931471805599453f * au;
+    if ((blk & 1) == 0) {   // view-1 row: positive pair with the same node's view-2 row
       const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
-      const uint4* zb = reinterpret_cast<const uint4*>(z + (size_t)(u + N) * D);
+      const uint4* zb = reinterpret_cast<const uint4*>(z + (size_t)(u + B) * D);
       float dot = 0.f;
       for (int c = 0; c < D / 8; ++c) {
         float fa[8], fb[8];
@@ -529,7 +281,7 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
       term -= 2.0f * 0.6931471805599453f * dot;
     }
   } else if (u < rows_pad_end) {
-    inv_r[u] = 0.f;
+    qw[u] = make_float2(0.f, 0.f);
   }
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
@@ -557,13 +309,13 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
 // may be issued into the buffer MMA2(t) still reads without waiting for MMA2(t) to complete.
 constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
-constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256;
+constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int rb0, int nrb, int ntiles,
-                   const float* __restrict__ inv_r /*[>= ntiles*128], zero padded*/, const float* __restrict__ gscale,
-                   const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
+                   const float2* __restrict__ qw /*[>= ntiles*128] (q_u, w_u), zero padded*/, const float* __restrict__ mu /*[D]*/,
+                   const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
   extern __shared__ uint8_t smem_raw[];
@@ -581,6 +333,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
   uint64_t* dz_full = p_full + 8;
   uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
+  float* s_rowsum = reinterpret_cast<float*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA) + 256);   // [2 warpgroups][128 rows]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -713,15 +466,16 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
     uint32_t tcount = 0, dzphase = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float cu = inv_r[row];  // padded with zeros beyond `rows`
+      const float2 cu = __ldg(qw + row);  // (q_u, w_u); padded with zeros beyond `rows`
       const int colbase = wg * 64;
+      float psum0 = 0.f, psum1 = 0.f;     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
         // every tile is split between the two warpgroups (64 columns each)
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        const float4* cvp = reinterpret_cast<const float4*>(inv_r + gcol0);
-        float4 cvr[16];  // 1/R of this tile's columns: fetched before the wait so the load latency is off the S -> P chain
+        const float4* cvp = reinterpret_cast<const float4*>(qw + gcol0);   // (q_v, w_v) pairs: one float4 = two columns
+        float4 cvr[16];  // first 32 columns: fetched before the wait so the load latency is off the S -> P chain
 #pragma unroll
         for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
         ptx::mbar_wait(&s_full[b], ph);
@@ -731,14 +485,15 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
         ptx::tmem_ld32(taddr + 32, r1);
         ptx::tmem_ld_wait();
         const bool diag = (row >= gcol0) && (row < gcol0 + 64);
+        // P_uv = 2^S (q_u w_v + q_v w_u)
         auto make_p = [&](const uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 cv = cvr[c * 8 + q];
-            float p0 = ex2(__uint_as_float(r[4 * q + 0])) * (cu + cv.x);
-            float p1 = ex2(__uint_as_float(r[4 * q + 1])) * (cu + cv.y);
-            float p2 = ex2(__uint_as_float(r[4 * q + 2])) * (cu + cv.z);
-            float p3 = ex2(__uint_as_float(r[4 * q + 3])) * (cu + cv.w);
+            const float4 c01 = cvr[2 * q], c23 = cvr[2 * q + 1];
+            float p0 = ex2(__uint_as_float(r[4 * q + 0])) * fmaf(cu.x, c01.y, c01.x * cu.y);
+            float p1 = ex2(__uint_as_float(r[4 * q + 1])) * fmaf(cu.x, c01.w, c01.z * cu.y);
+            float p2 = ex2(__uint_as_float(r[4 * q + 2])) * fmaf(cu.x, c23.y, c23.x * cu.y);
+            float p3 = ex2(__uint_as_float(r[4 * q + 3])) * fmaf(cu.x, c23.w, c23.z * cu.y);
             if (diag) {
               const int j = gcol0 + c * 32 + 4 * q;
               if (j + 0 == row) p0 = 0.f;
@@ -746,12 +501,16 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
               if (j + 2 == row) p2 = 0.f;
               if (j + 3 == row) p3 = 0.f;
             }
+            psum0 += p0 + p1;
+            psum1 += p2 + p3;
             pk[2 * q] = pack2(p0, p1);
             pk[2 * q + 1] = pack2(p2, p3);
           }
         };
         uint32_t pk[16];
         make_p(r0, 0, pk);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 16 + q);   // second 32 columns (L1-resident, lane-uniform)
         ptx::tmem_st16(taddr, pk);  // P (bf16 pairs) aliases this warpgroup's own, already consumed, S columns
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -764,263 +523,41 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, in
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + 2 + wg]);    // quarter 2/3: second 32 columns
       }
-      // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D)
+      // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D).  Both need the row sum of P over ALL
+      // columns: exchange the two warpgroups' halves through shared memory (the next row block cannot overwrite s_rowsum
+      // before every softmax warp has arrived on dz_empty, i.e. after its read below).
+      s_rowsum[wg * kBM + lrow] = psum0 + psum1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
       const int half = D / 2;
-      const int pair = (row < N) ? row + N : row - N;
+      const int blk = row / B;
+      const int pair = (blk & 1) ? row - B : row + B;
+      const bool valid = (blk >> 1) * B + (row - blk * B) < N;
       for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
-        if (row < rows) {
+        if (valid) {
           const uint4* zp = reinterpret_cast<const uint4*>(z + (size_t)pair * D + c0);
           float* out = dz + (size_t)row * D + c0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float f[8];
             unpack8(__ldg(zp + q), f);
-            float4 o0, o1;
-            o0.x = gcoef * (__uint_as_float(r[8 * q + 0]) - 2.f * f[0]);
-            o0.y = gcoef * (__uint_as_float(r[8 * q + 1]) - 2.f * f[1]);
-            o0.z = gcoef * (__uint_as_float(r[8 * q + 2]) - 2.f * f[2]);
-            o0.w = gcoef * (__uint_as_float(r[8 * q + 3]) - 2.f * f[3]);
-            o1.x = gcoef * (__uint_as_float(r[8 * q + 4]) - 2.f * f[4]);
-            o1.y = gcoef * (__uint_as_float(r[8 * q + 5]) - 2.f * f[5]);
-            o1.z = gcoef * (__uint_as_float(r[8 * q + 6]) - 2.f * f[6]);
-            o1.w = gcoef * (__uint_as_float(r[8 * q + 7]) - 2.f * f[7]);
-            *reinterpret_cast<float4*>(out + 8 * q) = o0;
-            *reinterpret_cast<float4*>(out + 8 * q + 4) = o1;
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(dz_empty);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
-}
-
-// ----------------------------------------------------------------------------
-// backward, variant B: 64-row column tiles with the stationary block in TMEM
-// ----------------------------------------------------------------------------
-// MMA1 in the SS form reads 4 KB (A) + 4 KB (B) of shared memory per 64 tensor cycles = the full 128 B/clk smem port, so it
-// cannot run at rate next to the TMA writes.  Here A lives in TMEM (TS form: 64 B/clk) and, TMEM being full (dZ 256 + A 128
-// columns), the S/P buffers shrink to 2 x 64 columns -> column tiles of 64 rows; the freed 64 KB of smem buy 5 TMA stages.
-// TMEM map: [0,256) dZ, [256,384) A (bf16), [384,448) S/P buffer 0, [448,512) S/P buffer 1.
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd64_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int N, int rb0, int nrb, int ntiles,
-                     const float* __restrict__ inv_r /*[>= ntiles*64], zero padded*/, const float* __restrict__ gscale,
-                     const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
-  constexpr int D = NP * kPanelElems;
-  constexpr int kPB = kBwdPanelBytes;                 // 64 rows x 128 B
-  constexpr uint32_t kStageBytes = kPB * kMaxPanels;  // 32 KB
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
-  uint8_t* sB = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStageBytes * kBwdStages);
-  uint64_t* full = bars;                    // [kBwdStages]
-  uint64_t* empty = full + kBwdStages;      // [kBwdStages]
-  uint64_t* a_full = empty + kBwdStages;    // 4 warp arrivals
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* s_full = a_empty + 1;           // [2]
-  uint64_t* p_full = s_full + 2;            // [2] 8 warp arrivals
-  uint64_t* dz_full = p_full + 2;
-  uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kBwdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&p_full[s], 8); }
-    ptx::mbar_init(a_full, 4);
-    ptx::mbar_init(a_empty, 1);
-    ptx::mbar_init(dz_full, 1);
-    ptx::mbar_init(dz_empty, 8);
-    ptx::fence_barrier_init();
-    ptx::prefetch_tensormap(&tmap);
-  }
-  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t tile_bytes = (uint32_t)NP * kPB;
-  constexpr uint32_t kColA = 256u, kColS = 384u;
-
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      int stage = 0;
-      uint32_t sphase = 0;
-      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
-        for (int ct = 0; ct < ntiles; ++ct) {
-          ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
-          uint8_t* dst = sB + (size_t)stage * kStageBytes;
-#pragma unroll
-          for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBNb);
-          if (++stage == kBwdStages) { stage = 0; sphase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {  // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
-      constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBNb, 0, 0);  // S = A V^T   (A tmem, B K-major)
-      constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);     // dZ += P V   (A tmem, B MN-major)
-      const uint32_t sb0 = ptx::smem_u32(sB);
-      const uint64_t bdesc_k0 = ptx::smem_desc_sw128(sb0, 16, 1024);
-      const uint64_t bdesc_mn0 = ptx::smem_desc_sw128(sb0, kPB, 1024);
-      uint32_t aphase = 0, dzphase = 0;
-      uint32_t tc1 = 0, st1 = 0, ph1 = 0;  // next tile for MMA1: global count, smem stage, stage phase
-      uint32_t tc2 = 0, st2 = 0;           // next tile for MMA2
-      auto issue_mma1 = [&]() {
-        const uint32_t b = tc1 & 1u;
-        ptx::mbar_wait(&full[st1], ph1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + kColS + b * 64u;
-        const uint64_t bd = bdesc_k0 + (uint64_t)(st1 * (kStageBytes >> 4));
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < NP * 4; ++kk) {
-            const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
-            ptx::umma_ts(d_tmem, tmem_base + kColA + (uint32_t)kk * 8u, bd + off16, idesc1, kk > 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(&s_full[b]);
-        }
-        __syncwarp();
-        ++tc1;
-        if (++st1 == (uint32_t)kBwdStages) { st1 = 0; ph1 ^= 1u; }
-      };
-      auto issue_mma2 = [&](bool first) {
-        const uint32_t b = tc2 & 1u, ph = (tc2 >> 1) & 1u;
-        ptx::mbar_wait(&p_full[b], ph);
-        ptx::tc_fence_after();
-        const uint64_t bmn = bdesc_mn0 + (uint64_t)(st2 * (kStageBytes >> 4));
-        const uint32_t p_tmem = tmem_base + kColS + b * 64u;
-        // K = 64 rows of the V tile, 16 per step; P of columns [32w, 32w+32) sits in TMEM columns [32w, 32w+16)
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kBNb / 16; ++k) {
-            ptx::umma_ts(tmem_base, p_tmem + (uint32_t)(k >> 1) * 32u + (uint32_t)(k & 1) * 8u, bmn + (uint32_t)(k * 2048 >> 4), idesc2,
-                         (!first || k > 0) ? 1u : 0u);
-          }
-          ptx::umma_commit(&empty[st2]);
-        }
-        __syncwarp();
-        ++tc2;
-        if (++st2 == (uint32_t)kBwdStages) st2 = 0;
-      };
-      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
-        ptx::mbar_wait(a_full, aphase);
-        aphase ^= 1;
-        ptx::mbar_wait(dz_empty, dzphase ^ 1);
-        ptx::tc_fence_after();
-        issue_mma1();
-        if (ntiles > 1) issue_mma1();
-        for (int ct = 0; ct < ntiles; ct += 2) {
-          issue_mma2(ct == 0);
-          if (ct + 1 < ntiles) issue_mma2(false);
-          if (ct + 2 < ntiles) issue_mma1();
-          if (ct + 3 < ntiles) issue_mma1();
-        }
-        if (ptx::elect_one()) {
-          ptx::umma_commit(dz_full);
-          ptx::umma_commit(a_empty);
-        }
-        __syncwarp();
-        dzphase ^= 1;
-      }
-    }
-  } else {  // ---------------- softmax / epilogue warpgroups ----------------
-    const int wg = (warp - 2) >> 2;
-    const int quarter = warp & 3;
-    const int lrow = quarter * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
-    uint32_t tcount = 0, dzphase = 0, aphase = 0;
-    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
-      const int row = rb * kBM + lrow;
-      if (wg == 0) {
-        ptx::mbar_wait(a_empty, aphase ^ 1);
-        aphase ^= 1;
-        ptx::tc_fence_after();
-        stage_rows_to_tmem(z, rows, D, row, lane_base + kColA);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(a_full);
-      }
-      const float cu = inv_r[row];  // padded with zeros beyond `rows`
-      const int colbase = wg * 32;
-      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
-        const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
-        const uint32_t taddr = lane_base + kColS + b * 64u + (uint32_t)colbase;
-        const int gcol0 = ct * kBNb + colbase;  // global column (row of Z) of r[0]
-        const float4* cvp = reinterpret_cast<const float4*>(inv_r + gcol0);
-        float4 cvr[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) cvr[q] = __ldg(cvp + q);
-        ptx::mbar_wait(&s_full[b], ph);
-        ptx::tc_fence_after();
-        uint32_t r[32], pk[16];
-        ptx::tmem_ld32(taddr, r);
-        ptx::tmem_ld_wait();
-        const bool diag = (row >= gcol0) && (row < gcol0 + 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 cv = cvr[q];
-          float p0 = ex2(__uint_as_float(r[4 * q + 0])) * (cu + cv.x);
-          float p1 = ex2(__uint_as_float(r[4 * q + 1])) * (cu + cv.y);
-          float p2 = ex2(__uint_as_float(r[4 * q + 2])) * (cu + cv.z);
-          float p3 = ex2(__uint_as_float(r[4 * q + 3])) * (cu + cv.w);
-          if (diag) {
-            const int j = gcol0 + 4 * q;
-            if (j + 0 == row) p0 = 0.f;
-            if (j + 1 == row) p1 = 0.f;
-            if (j + 2 == row) p2 = 0.f;
-            if (j + 3 == row) p3 = 0.f;
-          }
-          pk[2 * q] = pack2(p0, p1);
-          pk[2 * q + 1] = pack2(p2, p3);
-        }
-        ptx::tmem_st16(taddr, pk);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[b]);
-      }
-      ptx::mbar_wait(dz_full, dzphase);
-      dzphase ^= 1;
-      ptx::tc_fence_after();
-      constexpr int half = D / 2;
-      const int pair = (row < N) ? row + N : row - N;
-      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (row < rows) {
-          const uint4* zp = reinterpret_cast<const uint4*>(z + (size_t)pair * D + c0);
-          float* out = dz + (size_t)row * D + c0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float f[8];
-            unpack8(__ldg(zp + q), f);
-            float4 o0, o1;
-            o0.x = gcoef * (__uint_as_float(r[8 * q + 0]) - 2.f * f[0]);
-            o0.y = gcoef * (__uint_as_float(r[8 * q + 1]) - 2.f * f[1]);
-            o0.z = gcoef * (__uint_as_float(r[8 * q + 2]) - 2.f * f[2]);
-            o0.w = gcoef * (__uint_as_float(r[8 * q + 3]) - 2.f * f[3]);
-            o1.x = gcoef * (__uint_as_float(r[8 * q + 4]) - 2.f * f[4]);
-            o1.y = gcoef * (__uint_as_float(r[8 * q + 5]) - 2.f * f[5]);
-            o1.z = gcoef * (__uint_as_float(r[8 * q + 6]) - 2.f * f[6]);
-            o1.w = gcoef * (__uint_as_float(r[8 * q + 7]) - 2.f * f[7]);
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + c0 + 8 * q));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mu + c0 + 8 * q + 4));
+            float4 o0, o1;   // sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair
+            o0.x = gcoef * (fmaf(m0.x, prow, __uint_as_float(r[8 * q + 0])) - 2.f * f[0]);
+            o0.y = gcoef * (fmaf(m0.y, prow, __uint_as_float(r[8 * q + 1])) - 2.f * f[1]);
+            o0.z = gcoef * (fmaf(m0.z, prow, __uint_as_float(r[8 * q + 2])) - 2.f * f[2]);
+            o0.w = gcoef * (fmaf(m0.w, prow, __uint_as_float(r[8 * q + 3])) - 2.f * f[3]);
+            o1.x = gcoef * (fmaf(m1.x, prow, __uint_as_float(r[8 * q + 4])) - 2.f * f[4]);
+            o1.y = gcoef * (fmaf(m1.y, prow, __uint_as_float(r[8 * q + 5])) - 2.f * f[5]);
+            o1.z = gcoef * (fmaf(m1.z, prow, __uint_as_float(r[8 * q + 6])) - 2.f * f[6]);
+            o1.w = gcoef * (fmaf(m1.w, prow, __uint_as_float(r[8 * q + 7])) - 2.f * f[7]);
             *reinterpret_cast<float4*>(out + 8 * q) = o0;
             *reinterpret_cast<float4*>(out + 8 * q + 4) = o1;
           }
@@ -1093,6 +630,13 @@ static Schedule make_schedule(int64_t rows, int64_t row_begin, int64_t row_end) 
   return s;
 }
 
+// The opt-in dynamic shared-memory size is a per-device function attribute and the library supports one device per host
+// thread (bmkg_bind_device): set it on every launch (a cheap driver call) instead of caching a process-wide flag.
+template <typename K>
+static bool set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
 }  // namespace nce
 }  // namespace bmkg
 
@@ -1103,54 +647,47 @@ extern "C" {
 
 int bmkg_last_driver_status(void) { return g_last_driver_status; }
 
-int64_t bmkg_infonce_padded_rows(int64_t N) { return ceil_div(2 * N, kBN) * kBN; }
+// total rows of the block-interleaved stacked layout, and the same padded to whole 128-row tiles
+static int64_t stacked_rows(int64_t N, int64_t B) { return 2 * B * ceil_div(N, B); }
+int64_t bmkg_infonce_stacked_rows(int64_t N, int64_t B) { return (N > 0 && B > 0) ? stacked_rows(N, B) : 0; }
+int64_t bmkg_infonce_padded_rows(int64_t N, int64_t B) { return (N > 0 && B > 0) ? ceil_div(stacked_rows(N, B), kBN) * kBN : 0; }
 
 static bool rows_range_ok(int64_t rows, int64_t b, int64_t e) {
   return b >= 0 && b < e && e <= rows && b % kBM == 0 && (e % kBM == 0 || e == rows);
 }
 
-// BMKG_INFONCE_FWD=tri selects the upper-triangle forward for full-range launches (read once per process)
-static bool fwd_tri_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BMKG_INFONCE_FWD");
-    v = (e && e[0] == 't') ? 1 : 0;
-  }
-  return v == 1;
-}
-static int64_t fwd_slots(const Schedule& s, bool tri) { return 2 * (int64_t)s.nchunks + (tri ? 2 * kNumSMs : 0); }
+// partial row sums [2 * nchunks][padded rows] + per-CTA loss partials; nchunks depends on how many row blocks the launch owns
+static bool block_ok(int64_t N, int64_t B) { return N > 0 && B > 0 && (B == N || B % kBM == 0) && stacked_rows(N, B) < (1ll << 30); }
 
-// partial row sums [2 * nchunks][padded rows] (+ [2 * SMs][padded rows] column-sum slots for the triangular forward) + per-CTA
-// loss partials; nchunks depends on how many row blocks the launch owns
-size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int D, int64_t row_begin, int64_t row_end) {
+size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end) {
   (void)D;
-  const int64_t rows = 2 * N;
+  if (!block_ok(N, B)) return 0;
+  const int64_t rows = stacked_rows(N, B);
   if (!rows_range_ok(rows, row_begin, row_end)) return 0;
   Schedule s = make_schedule(rows, row_begin, row_end);
-  const int64_t rp = bmkg_infonce_padded_rows(N);
+  const int64_t rp = bmkg_infonce_padded_rows(N, B);
   WsCarver c(nullptr);
-  c.take<float>((size_t)fwd_slots(s, fwd_tri_enabled() && row_begin == 0 && row_end == rows) * rp);
+  c.take<float>((size_t)2 * s.nchunks * rp);
   c.take<float>((size_t)ceil_div(rp, 256));
   return c.used();
 }
 
-size_t bmkg_infonce_workspace_bytes(int64_t N, int D) { return bmkg_infonce_workspace_bytes_rows(N, D, 0, 2 * N); }
+size_t bmkg_infonce_workspace_bytes(int64_t N, int D) { return bmkg_infonce_workspace_bytes_rows(N, N, D, 0, 2 * N); }
 
-int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begin, int64_t row_end, float* loss, float* inv_r,
-                          void* ws, size_t ws_bytes, void* stream) {
-  BMKG_REQUIRE(z_bf16 && loss && inv_r && N > 0, BMKG_ERR_BAD_ARG);
+int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end,
+                          float* loss, float* qw, void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(z_bf16 && a && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
-  BMKG_REQUIRE(aligned16(z_bf16), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(qw), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rows = 2 * N;
+  const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
-  BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes_rows(N, D, row_begin, row_end), BMKG_ERR_WORKSPACE);
-  const int64_t rp = bmkg_infonce_padded_rows(N);
+  BMKG_REQUIRE(ws && ws_bytes >= bmkg_infonce_workspace_bytes_rows(N, B, D, row_begin, row_end), BMKG_ERR_WORKSPACE);
+  const int64_t rp = bmkg_infonce_padded_rows(N, B);
   Schedule s = make_schedule(rows, row_begin, row_end);
-  const bool tri = fwd_tri_enabled() && row_begin == 0 && row_end == rows;
   WsCarver c(ws);
-  float* partial = c.take<float>((size_t)fwd_slots(s, tri) * rp);
+  const int nslots = 2 * s.nchunks;
+  float* partial = c.take<float>((size_t)nslots * rp);
   const int nb = (int)ceil_div(rp, 256);
   float* block_part = c.take<float>(nb);
 
@@ -1160,40 +697,10 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
   const int n_items = s.nrb * s.nchunks;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
-  int nslots = 2 * s.nchunks;
-  if (tri) {
-    // triangular forward: row-sum slots of skipped (row block, chunk) items and the per-(CTA, warpgroup) column-sum slots start at 0
-    nslots = 2 * s.nchunks + 2 * grid;
-    if (cudaMemsetAsync(partial, 0, (size_t)nslots * rp * sizeof(float), st) != cudaSuccess) return BMKG_ERR_LAUNCH;
-#define BMKG_LAUNCH_TRI(NP_)                                                                                                      \
-  {                                                                                                                               \
-    static bool attr_set = false;                                                                                                 \
-    if (!attr_set) {                                                                                                              \
-      if (cudaFuncSetAttribute(infonce_fwd_tri_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemBytes) !=   \
-          cudaSuccess)                                                                                                            \
-        return BMKG_ERR_LAUNCH;                                                                                                   \
-      attr_set = true;                                                                                                            \
-    }                                                                                                                             \
-    infonce_fwd_tri_kernel<NP_><<<grid, kThreads, kTriSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, partial);                \
-  }
-    switch (D / kPanelElems) {
-      case 1: BMKG_LAUNCH_TRI(1) break;
-      case 2: BMKG_LAUNCH_TRI(2) break;
-      case 3: BMKG_LAUNCH_TRI(3) break;
-      default: BMKG_LAUNCH_TRI(4) break;
-    }
-#undef BMKG_LAUNCH_TRI
-  } else {
-#define BMKG_LAUNCH_FWD(NP_)                                                                                                      \
-  {                                                                                                                               \
-    static bool attr_set = false;                                                                                                 \
-    if (!attr_set) {                                                                                                              \
-      if (cudaFuncSetAttribute(infonce_fwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes) !=       \
-          cudaSuccess)                                                                                                            \
-        return BMKG_ERR_LAUNCH;                                                                                                   \
-      attr_set = true;                                                                                                            \
-    }                                                                                                                             \
-    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, partial);                    \
+#define BMKG_LAUNCH_FWD(NP_)                                                                            \
+  {                                                                                                     \
+    if (!set_smem(infonce_fwd_kernel<NP_>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                      \
+    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, a, partial); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_FWD(1) break;
@@ -1202,79 +709,43 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, int64_t N, int D, int64_t row_begi
     default: BMKG_LAUNCH_FWD(4) break;
   }
 #undef BMKG_LAUNCH_FWD
-  }
   BMKG_CHECK_LAUNCH();
-  const float npad = (float)(s.ntiles * kBN - rows);
-  // rows of this launch: [row_begin, row_end); the zero padding of inv_r beyond 2N belongs to the launch that owns the last row
+  const float npad = (float)(s.ntiles * kBN - 2 * N);   // all-zero columns (layout padding + TMA out-of-range fill)
+  // rows of this launch: [row_begin, row_end); the zero padding of qw beyond 2N belongs to the launch that owns the last row
   const int64_t pad_end = (row_end == rows) ? rp : row_end;
   const int nbr = (int)ceil_div(pad_end - row_begin, 256);
   infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, nslots, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
-                                                    D, npad, static_cast<const __nv_bfloat16*>(z_bf16), inv_r, block_part);
+                                                    (int)B, D, npad, zp, a, reinterpret_cast<float2*>(qw), block_part);
   infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nbr, 1.0f / (2.0f * (float)N), loss);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, int64_t N, int D, float* loss, float* inv_r, void* ws, size_t ws_bytes, void* stream) {
-  return bmkg_infonce_fwd_rows(z_bf16, N, D, 0, 2 * N, loss, inv_r, ws, ws_bytes, stream);
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, int64_t N, int D, float* loss, float* qw, void* ws, size_t ws_bytes,
+                     void* stream) {
+  return bmkg_infonce_fwd_rows(z_bf16, a, N, N, D, 0, 2 * N, loss, qw, ws, ws_bytes, stream);
 }
 
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, int64_t row_begin,
-                          int64_t row_end, float* dz, void* stream) {
-  BMKG_REQUIRE(z_bf16 && inv_r && gscale && dz && N > 0, BMKG_ERR_BAD_ARG);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t N, int64_t B, int D,
+                          int64_t row_begin, int64_t row_end, float* dz, void* stream) {
+  BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(2 * N < (1ll << 30), BMKG_ERR_BAD_ARG);
-  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(inv_r), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rows = 2 * N;
-  // Two backward variants are kept for A/B measurement (profiles/): the default 128-wide tiles with an SS MMA1 (2.36 ms at
-  // N=28k on B200) and BMKG_INFONCE_BWD=ts64, 64-wide tiles with the stationary block in TMEM (2.50 ms).
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("BMKG_INFONCE_BWD");
-    variant = (e && e[0] == 't') ? 1 : 0;
-  }
+  const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
-  const int bn = variant ? kBNb : kBN;
   const int rb0 = (int)(row_begin / kBM);
-  const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, bn);
+  const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, kBN);
   CUtensorMap tmap;
-  int rc = make_z_tensormap(&tmap, z_bf16, rows, D, bn);
+  int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
   if (rc != BMKG_OK) return rc;
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
-  if (variant) {
-#define BMKG_LAUNCH_BWD64(NP_)                                                                                                    \
-  {                                                                                                                               \
-    static bool attr_set = false;                                                                                                 \
-    if (!attr_set) {                                                                                                              \
-      if (cudaFuncSetAttribute(infonce_bwd64_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes) !=     \
-          cudaSuccess)                                                                                                            \
-        return BMKG_ERR_LAUNCH;                                                                                                   \
-      attr_set = true;                                                                                                            \
-    }                                                                                                                             \
-    infonce_bwd64_kernel<NP_><<<grid, kThreads, kBwdSmemBytes, st>>>(tmap, (int)rows, (int)N, rb0, nrb, ntiles, inv_r, gscale, zp, dz); \
-  }
-    switch (D / kPanelElems) {
-      case 1: BMKG_LAUNCH_BWD64(1) break;
-      case 2: BMKG_LAUNCH_BWD64(2) break;
-      case 3: BMKG_LAUNCH_BWD64(3) break;
-      default: BMKG_LAUNCH_BWD64(4) break;
-    }
-#undef BMKG_LAUNCH_BWD64
-    BMKG_CHECK_LAUNCH();
-    return BMKG_OK;
-  }
-#define BMKG_LAUNCH_BWD(NP_)                                                                                                      \
-  {                                                                                                                               \
-    static bool attr_set = false;                                                                                                 \
-    if (!attr_set) {                                                                                                              \
-      if (cudaFuncSetAttribute(infonce_bwd_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytesA) !=      \
-          cudaSuccess)                                                                                                            \
-        return BMKG_ERR_LAUNCH;                                                                                                   \
-      attr_set = true;                                                                                                            \
-    }                                                                                                                             \
-    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)rows, (int)N, rb0, nrb, ntiles, inv_r, gscale, zp, dz); \
+  const float2* qwp = reinterpret_cast<const float2*>(qw);
+#define BMKG_LAUNCH_BWD(NP_)                                                                                        \
+  {                                                                                                                 \
+    if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \
+    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_BWD(1) break;
@@ -1287,8 +758,9 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* inv_r, const float* g
   return BMKG_OK;
 }
 
-int bmkg_infonce_bwd(const void* z_bf16, const float* inv_r, const float* gscale, int64_t N, int D, float* dz, void* stream) {
-  return bmkg_infonce_bwd_rows(z_bf16, inv_r, gscale, N, D, 0, 2 * N, dz, stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t N, int D, float* dz,
+                     void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, qw, mu, gscale, N, N, D, 0, 2 * N, dz, stream);
 }
 
 }  // extern "C"

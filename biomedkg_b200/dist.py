@@ -1,19 +1,23 @@
-"""Row-sharded GRACE InfoNCE across the GPUs of one node.
+"""Row-sharded GRACE step across the GPUs of one node ("partition nodes by destination row").
 
-The stacked views Z = [a; b] (2N x D) are available on every rank (in round 1 the encoder is data-replicated; a row-sharded
-encoder would all-gather them - the InfoNCE side is the same).  Rank p owns a contiguous, 128-aligned block of Z's rows and
+Partition.  Nodes are cut into ``world`` contiguous blocks of B rows, B = ceil(N / world) rounded up to 128 (``shard_layout``).
+Rank p owns the nodes [pB, (p+1)B) in BOTH views, so
 
-    forward :  R_u for its rows against ALL columns (tcgen05 kernel on a row range)
-               all_gather(1/R)            - the backward needs 1/R_v of every column
-               all_reduce(loss share)     - scalar
-    backward:  dZ rows of its block (needs the gathered 1/R), then all_gather(dZ) so every rank continues the (replicated)
-               backward with the full gradient.
+  * encoder: fusion, feature masks, every layer's GEMMs and the projector run on the rank's rows only; each conv layer
+    all-gathers its transformed rows (bf16 [N,C]) and aggregates its own destination rows; the backward all-gathers the
+    pre-activation gradient and aggregates its own SOURCE rows over the CSC (gather form both ways: no scatter, no atomics);
+  * InfoNCE: the stacked operand uses the block-interleaved layout of include/bmkg_b200.h with view block B - one
+    all-gather of every rank's [2, B, D] block assembles it, and a rank's rows of both views are one contiguous 128-aligned
+    range [2pB, 2(p+1)B).  forward: all-reduce of the [D] column sums (common vector mu), all-gather of the bf16
+    deviations Z and of a = mu . d, the row-range tcgen05 kernel, all-gather of (q, w) (2 floats per row), all-reduce of the
+    scalar loss share.  backward: the row-range kernel writes dZ of exactly the rows whose h this rank holds - NO collective.
+  * parameter gradients are partial sums over the rank's rows -> one flat all-reduce (``allreduce_grads``).
 
-The result equals the single-GPU full-graph loss (unlike the reference's DDP, which contrasts per rank mini-batch).  No
-collective touches the N x N work itself; only 2N floats and the 2N x D gradient cross NVLink.
+The result is the single-GPU full-graph loss (unlike the reference's DDP, which contrasts per rank mini-batch).  No
+collective touches the N x N work.
 
-The compute is injected (``impl``): the default calls the CUDA kernels; the gloo CPU tests inject a torch restatement so
-the partitioning / collective / autograd plumbing is exercised with world_size 2 on CPU.
+The compute is injected (``impl``): the default calls the CUDA kernels; the gloo CPU tests inject a torch restatement of
+the same row-range math so the partitioning / collective / autograd plumbing is exercised with world_size 2 on CPU.
 """
 from __future__ import annotations
 
@@ -26,98 +30,164 @@ ROW_ALIGN = 128
 LOG2E = 1.4426950408889634
 
 
-def row_partition(num_rows: int, world: int, align: int = ROW_ALIGN):
-    """Contiguous [begin, end) row ranges, begins aligned to ``align``, sizes within one aligned block of each other.
-    Ranks beyond the number of aligned blocks get an empty range."""
-    blocks = (num_rows + align - 1) // align
-    out = []
-    for r in range(world):
-        b0 = (blocks * r) // world
-        b1 = (blocks * (r + 1)) // world
-        out.append((min(b0 * align, num_rows), min(b1 * align, num_rows)))
-    return out
+def shard_layout(num_nodes: int, world: int, align: int = ROW_ALIGN):
+    """-> (B, [(n0, n1)] per rank): equal node blocks of B rows, B a multiple of ``align``; trailing ranks may be short / empty."""
+    B = (num_nodes + world - 1) // world
+    B = max(align, (B + align - 1) // align * align)
+    return B, [(min(p * B, num_nodes), min((p + 1) * B, num_nodes)) for p in range(world)]
+
+
+def node_partition(num_nodes: int, world: int):
+    """Node blocks of the row-sharded step (same as ``shard_layout``; kept under the name loaders use)."""
+    return shard_layout(num_nodes, world)
 
 
 class CudaImpl:
-    """Kernels from libbmkg_b200.so on a row range."""
+    """Kernels from libbmkg_b200.so on this rank's rows."""
 
-    def prep(self, h1, h2, tau):
-        from . import ops
-        from .ops import _p, _stream, call
-
-        N, D = h1.shape
-        scale = math.sqrt(LOG2E / tau)
-        z = torch.empty(2 * N, D, dtype=torch.bfloat16, device=h1.device)
-        inv_norm = torch.empty(2 * N, dtype=torch.float32, device=h1.device)
-        call("bmkg_l2norm_scale", _p(h1), N, D, scale, _p(z), _p(inv_norm), _stream())
-        call("bmkg_l2norm_scale", _p(h2), N, D, scale, z.data_ptr() + N * D * 2, inv_norm.data_ptr() + N * 4, _stream())
-        return z, inv_norm, scale
-
-    def fwd_rows(self, z, N, r0, r1):
+    def stats(self, h):
+        """h fp32 [n, D] -> (inv_norm [n], column sums of the normalised rows [D])"""
         from .ops import _p, _stream, _ws, call, lib
 
-        D = z.size(1)
-        loss = torch.zeros((), dtype=torch.float32, device=z.device)
-        inv_r = torch.zeros(lib.bmkg_infonce_padded_rows(N), dtype=torch.float32, device=z.device)
-        if r1 > r0:
-            ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, D, r0, r1), z.device)
-            call("bmkg_infonce_fwd_rows", _p(z), N, D, r0, r1, _p(loss), _p(inv_r), _p(ws), ws.numel(), _stream())
-        return loss, inv_r
+        n, D = h.shape
+        inv = torch.empty(max(n, 1), dtype=torch.float32, device=h.device)
+        cs = torch.zeros(D, dtype=torch.float32, device=h.device)
+        if n > 0:
+            ws = _ws(lib.bmkg_colsum_workspace_bytes(n, D), h.device)
+            call("bmkg_l2norm_colsum", _p(h), n, D, _p(inv), _p(cs), _p(ws), ws.numel(), _stream())
+        return inv, cs
 
-    def bwd_rows(self, z, inv_r, g, N, r0, r1):
+    def center(self, hs, invs, mu, B, scale):
+        """-> (bf16 [2, B, D] deviations, fp32 [2, B] a = mu . d); rows beyond the rank's nodes stay zero"""
         from .ops import _p, _stream, call
 
-        D = z.size(1)
-        dz = torch.zeros(2 * N, D, dtype=torch.float32, device=z.device)
+        D = hs[0].size(1)
+        z = torch.zeros(2, B, D, dtype=torch.bfloat16, device=mu.device)
+        a = torch.zeros(2, B, dtype=torch.float32, device=mu.device)
+        for v, (h, inv) in enumerate(zip(hs, invs)):
+            if h.size(0) > 0:
+                call("bmkg_center_scale", _p(h), _p(inv), _p(mu), h.size(0), D, scale, _p(z[v]), _p(a[v]), _stream())
+        return z, a
+
+    def fwd_rows(self, Z, A, N, B, r0, r1):
+        """Z bf16 [R_all, D], A fp32 [R_all] -> (loss share, qw [R_all, 2] with rows [r0, r1) filled)"""
+        from .ops import _p, _stream, _ws, call, lib
+
+        D = Z.size(1)
+        loss = torch.zeros((), dtype=torch.float32, device=Z.device)
+        qw = torch.zeros(Z.size(0), 2, dtype=torch.float32, device=Z.device)
         if r1 > r0:
-            call("bmkg_infonce_bwd_rows", _p(z), _p(inv_r), _p(g), N, D, r0, r1, _p(dz), _stream())
+            ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
+            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), N, B, D, r0, r1, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
+        return loss, qw
+
+    def bwd_rows(self, Z, QW, mu, g, N, B, r0, r1):
+        """-> dZ fp32 [r1 - r0, D] of this range (the kernel addresses dz by global row: pass the buffer shifted by -r0 rows)"""
+        from .ops import _p, _stream, call
+
+        D = Z.size(1)
+        dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
+        if r1 > r0:
+            call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), N, B, D, r0, r1, dz.data_ptr() - r0 * D * 4, _stream())
         return dz
 
-    def norm_bwd(self, h1, h2, inv_norm, dz, scale):
+    def norm_bwd(self, h, inv, dz, scale):
         from .ops import _p, _stream, call
 
-        N, D = h1.shape
-        dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
-        call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, scale, _p(dh1), _stream())
-        call("bmkg_l2norm_scale_bwd", _p(h2), inv_norm.data_ptr() + N * 4, dz.data_ptr() + N * D * 4, N, D, scale, _p(dh2), _stream())
-        return dh1, dh2
+        dh = torch.empty_like(h)
+        if h.size(0) > 0:
+            call("bmkg_l2norm_scale_bwd", _p(h), _p(inv), _p(dz), h.size(0), h.size(1), scale, _p(dh), _stream())
+        return dh
 
 
 class _ShardedInfoNCEFn(torch.autograd.Function):
+    """h1_loc, h2_loc: this rank's node rows [n0, n1) of the two projected views; N: total nodes."""
+
     @staticmethod
-    def forward(ctx, h1, h2, tau, group, impl):
+    def forward(ctx, h1, h2, N, tau, group, impl):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        h1, h2 = h1.contiguous().float(), h2.contiguous().float()
-        N = h1.size(0)
-        parts = row_partition(2 * N, world)
-        r0, r1 = parts[rank]
-        z, inv_norm, scale = impl.prep(h1, h2, tau)
-        loss, inv_r = impl.fwd_rows(z, N, r0, r1)
-        # every rank filled only its own rows of inv_r (zeros elsewhere): a sum all-reduce is the all-gather of ragged blocks
-        dist.all_reduce(inv_r, group=group)
+        h1, h2 = h1.contiguous(), h2.contiguous()           # fp32 for the CUDA kernels (the CPU test impl runs fp64)
+        B, parts = shard_layout(N, world)
+        n0, n1 = parts[rank]
+        if h1.size(0) != n1 - n0 or h2.size(0) != n1 - n0:
+            raise ValueError(f"rank {rank} must pass its node block [{n0}, {n1}) of both views")
+        D = h1.size(1)
+        dev = h1.device
+        scale = math.sqrt(LOG2E / tau)
+        inv1, cs1 = impl.stats(h1)
+        inv2, cs2 = impl.stats(h2)
+        cs = cs1 + cs2
+        dist.all_reduce(cs, group=group)                       # every rank must centre with the same common vector
+        mu = (cs * (scale / (2.0 * N))).contiguous()
+        zb, ab = impl.center((h1, h2), (inv1, inv2), mu, B, scale)
+        R_all = world * 2 * B                                  # >= bmkg_infonce_padded_rows(N, B); trailing blocks all zero
+        Z = torch.empty(R_all, D, dtype=zb.dtype, device=dev)
+        A = torch.empty(R_all, dtype=ab.dtype, device=dev)
+        dist.all_gather_into_tensor(Z, zb.view(2 * B, D), group=group)
+        dist.all_gather_into_tensor(A, ab.view(2 * B), group=group)
+        nblk = (N + B - 1) // B
+        r0, r1 = (rank * 2 * B, (rank + 1) * 2 * B) if rank < nblk else (0, 0)
+        loss, qw = impl.fwd_rows(Z, A, N, B, r0, r1)
+        QW = torch.empty(R_all, 2, dtype=qw.dtype, device=dev)
+        dist.all_gather_into_tensor(QW, qw[rank * 2 * B: (rank + 1) * 2 * B].contiguous(), group=group)
         dist.all_reduce(loss, group=group)
-        ctx.save_for_backward(h1, h2, z, inv_norm, inv_r)
-        ctx.meta = (scale, group, impl, N, r0, r1)
+        ctx.save_for_backward(h1, h2, inv1, inv2, Z, QW, mu)
+        ctx.meta = (scale, impl, N, B, r0, r1)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        h1, h2, z, inv_norm, inv_r = ctx.saved_tensors
-        scale, group, impl, N, r0, r1 = ctx.meta
-        dz = impl.bwd_rows(z, inv_r, g.contiguous().float(), N, r0, r1)
-        dist.all_reduce(dz, group=group)          # rows are disjoint across ranks: sum == all-gather
-        dh1, dh2 = impl.norm_bwd(h1, h2, inv_norm, dz, scale)
-        return dh1, dh2, None, None, None
+        h1, h2, inv1, inv2, Z, QW, mu = ctx.saved_tensors
+        scale, impl, N, B, r0, r1 = ctx.meta
+        n = h1.size(0)
+        dz = impl.bwd_rows(Z, QW, mu, g.contiguous().to(h1.dtype), N, B, r0, r1)     # rows of THIS rank's nodes: no collective
+        dh1 = impl.norm_bwd(h1, inv1, dz[:n], scale)
+        dh2 = impl.norm_bwd(h2, inv2, dz[B: B + n] if n > 0 else dz[:0], scale)
+        return dh1, dh2, None, None, None, None
+
+
+def sharded_infonce_local(h1_loc, h2_loc, num_nodes, tau=0.2, group=None, impl=None):
+    """InfoNCE of the full graph from this rank's node rows of the two views (see the module docstring)."""
+    from . import ops
+
+    if impl is None:
+        h1_loc, h2_loc = ops.pad_infonce_dim(h1_loc.float(), h2_loc.float())
+        impl = CudaImpl()
+    return _ShardedInfoNCEFn.apply(h1_loc, h2_loc, int(num_nodes), float(tau), group, impl)
+
+
+class _LocalRowsFn(torch.autograd.Function):
+    """Replicated [N, D] -> this rank's rows.  Downstream every rank computes ITS rows' share of one global loss, so the
+    gradient of the replicated tensor is the concatenation of the ranks' row gradients: backward = all-gather."""
+
+    @staticmethod
+    def forward(ctx, full, n0, n1, B, group):
+        ctx.meta = (n0, n1, B, group, full.size(0))
+        return full[n0:n1].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        n0, n1, B, group, N = ctx.meta
+        world = dist.get_world_size(group)
+        blk = torch.zeros(B, g.size(1), dtype=g.dtype, device=g.device)
+        blk[: n1 - n0] = g
+        out = torch.empty(world * B, g.size(1), dtype=g.dtype, device=g.device)
+        dist.all_gather_into_tensor(out, blk, group=group)
+        return out[:N], None, None, None, None
 
 
 def sharded_infonce_loss(h1, h2, tau=0.2, group=None, impl=None):
     """DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True)(h1, h2) with the 2N x 2N work split by rows over ``group``.
-    h1, h2 must be identical on every rank (replicated encoder) and so is the returned loss / gradient."""
+    h1, h2 are REPLICATED (identical on every rank - e.g. a replicated GAT encoder) and so is the returned loss / gradient."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         from . import ops
 
         return ops.infonce_loss(h1, h2, tau)
-    return _ShardedInfoNCEFn.apply(h1, h2, float(tau), group, impl or CudaImpl())
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    N = h1.size(0)
+    B, parts = shard_layout(N, world)
+    n0, n1 = parts[rank]
+    return sharded_infonce_local(_LocalRowsFn.apply(h1, n0, n1, B, group), _LocalRowsFn.apply(h2, n0, n1, B, group), N, tau, group, impl)
 
 
 class ShardedDualBranchContrast(torch.nn.Module):
@@ -132,14 +202,8 @@ class ShardedDualBranchContrast(torch.nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
-# Row-sharded GCN encoder + full GRACE step ("partition nodes by destination row")
+# Row-sharded GCN encoder + full GRACE step
 # ---------------------------------------------------------------------------------------------------------------------------
-def node_partition(num_nodes: int, world: int):
-    """Equal contiguous node blocks (the last ones may be short / empty): block p = [p*B, min((p+1)*B, N)), B = ceil(N / world)."""
-    B = (num_nodes + world - 1) // world
-    return B, [(min(p * B, num_nodes), min((p + 1) * B, num_nodes)) for p in range(world)]
-
-
 def _all_gather_rows(local: torch.Tensor, num_rows: int, block: int, group) -> torch.Tensor:
     """[n_local, C] blocks of every rank -> [num_rows, C] (NCCL all-gather of equal, zero-padded blocks)."""
     world = dist.get_world_size(group)
@@ -172,14 +236,15 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
     local dW (summed over ranks by the caller), local dX.  Gather form in both directions: no scatter, no atomics."""
 
     @staticmethod
-    def forward(ctx, x_loc, weight, bias, view, r0, r1, num_nodes, block, group, relu, drop_p, drop_seed, out_fp32):
+    def forward(ctx, x_loc, weight, bias, view, r0, r1, num_nodes, block, group, relu, drop_p, drop_seed, drop_keep, out_fp32, correct):
         from . import ops
 
         w16 = weight.to(torch.bfloat16)
-        xw_loc = torch.mm(x_loc, w16.t())
+        # the weight-residual correction uses the mean of the LOCAL rows: any common vector restores the rounded-away part
+        xw_loc = ops._xw(x_loc, weight, w16, correct and x_loc.size(0) > 0)
         xw = _all_gather_rows(xw_loc, num_nodes, block, group).contiguous()
         hub = view.hub_csr if view.hub_possible else None
-        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, None, out_fp32,
+        y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
                               hub_rows=hub, row_range=(r0, r1))
         ctx.meta = (view, r0, r1, num_nodes, block, group, relu, drop_p)
         ctx.save_for_backward(x_loc, w16, y if relu else None)
@@ -210,7 +275,7 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
         dxw = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, g_full, hub_rows=hub, row_range=(r0, r1))
         dw = ops._mm_f32(dxw.t(), x_loc) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
-        return (dx, dw, dbias) + (None,) * 10
+        return (dx, dw, dbias) + (None,) * 12
 
 
 def sharded_gcn_encoder(encoder, x_loc, view, r0, r1, num_nodes, block, group):
@@ -219,31 +284,36 @@ def sharded_gcn_encoder(encoder, x_loc, view, r0, r1, num_nodes, block, group):
     layers = encoder.graph_layers
     for i, layer in enumerate(layers):
         last = i == len(layers) - 1
-        p, seed = 0.0, 0
+        p, seed, keep = 0.0, 0, None
         if not last and encoder.drop_out and encoder.training:
             p = 0.2
-            seed, _ = encoder.draws.dropout((num_nodes, layer.out_channels), p, x.device)   # global-row hash: sharding-invariant
-        x = _ShardedGCNLayerFn.apply(x, layer.lin.weight, layer.bias, view, r0, r1, num_nodes, block, group, not last, p, seed, last)
+            # full-size draw in the reference's order (identical masks whatever the world size); an explicit mask (replayed
+            # or graph-safe draws) is sliced to this rank's rows, the counter-hash stream is indexed by the global row
+            seed, keep = encoder.draws.dropout((num_nodes, layer.out_channels), p, x.device)
+            if keep is not None:
+                keep = keep[r0:r1].contiguous()
+        x = _ShardedGCNLayerFn.apply(x, layer.lin.weight, layer.bias, view, r0, r1, num_nodes, block, group, not last, p, seed, keep,
+                                     last, i > 0)
     return x
 
 
 def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
     """GRACEModule.training_step's loss with the node rows split over the ranks of ``group``.
 
-    Every rank receives the same (x, edge_index) and the same parameters / RNG state.  Fusion, feature masks, the GCN layers'
+    Every rank receives the same edge_index and the same parameters / RNG state.  Fusion, feature masks, the GCN layers'
     GEMMs, the projector and the normalisation run on this rank's node block only; each GCN layer all-gathers its transformed
-    rows (bf16 [N,256] over NVLink) before aggregating its own destination rows; the projected views are all-gathered once and
-    the InfoNCE is split by rows of Z (sharded_infonce_loss).  The loss is the single-GPU full-graph loss; parameter gradients
-    are partial sums that the caller all-reduces (``allreduce_grads``).
+    rows (bf16 [N,256] over NVLink) before aggregating its own destination rows; the InfoNCE rows are the rank's own nodes in
+    both views (``sharded_infonce_local``).  The loss is the single-GPU full-graph loss; parameter gradients are partial sums
+    that the caller all-reduces (``allreduce_grads``).
 
     ``x`` is either the full feature tensor (every rank slices its rows) or, with ``num_nodes`` given, only this rank's block
-    ``node_partition(num_nodes, world)[1][rank]`` - a sharded loader then moves 1/world of the features per rank."""
+    ``shard_layout(num_nodes, world)[1][rank]`` - a sharded loader then moves 1/world of the features per rank."""
     from . import ops
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     model = module.model
     N = int(num_nodes) if num_nodes is not None else x.size(0)
-    block, parts = node_partition(N, world)
+    block, parts = shard_layout(N, world)
     r0, r1 = parts[rank]
     x_loc = x if num_nodes is not None else x[r0:r1]
     if x_loc.size(0) != r1 - r0:
@@ -262,9 +332,8 @@ def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
         sharded_gcn_encoder(enc, x0, sg.view(None), r0, r1, N, block, group)   # the reference's unused un-augmented view
     z1 = sharded_gcn_encoder(enc, x1, sg.view(k1), r0, r1, N, block, group)
     z2 = sharded_gcn_encoder(enc, x2, sg.view(k2), r0, r1, N, block, group)
-    h1 = _GatherRowsFn.apply(model.project(z1), N, block, r0, group)
-    h2 = _GatherRowsFn.apply(model.project(z2), N, block, r0, group)
-    return sharded_infonce_loss(h1, h2, module.contrast_model.loss.tau if hasattr(module.contrast_model, "loss") else 0.2, group)
+    tau = module.contrast_model.loss.tau if hasattr(module.contrast_model, "loss") else 0.2
+    return sharded_infonce_local(model.project(z1), model.project(z2), N, tau, group)
 
 
 def allreduce_grads(params, group=None):

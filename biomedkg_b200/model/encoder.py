@@ -44,11 +44,13 @@ class GCNConv(nn.Module):
         with torch.no_grad():
             self.bias.zero_()
 
-    def forward(self, x, edge_index, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=True):
+    def forward(self, x, edge_index, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=None, correct=False):
+        """``out_fp32`` defaults to fp32 output (as PyG) unless ``relu`` is fused (the encoder's bf16 inter-layer format)."""
         view = ops.as_view(edge_index, x.size(0))
         if x.dtype != ops.BF16:
             x = ops.mask_cast(x.float())[0]
-        return ops.gcn_layer(x, self.lin.weight, self.bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32)
+        out_fp32 = (not relu) if out_fp32 is None else out_fp32
+        return ops.gcn_layer(x, self.lin.weight, self.bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32, correct)
 
 
 class GATConv(nn.Module):
@@ -73,12 +75,13 @@ class GATConv(nn.Module):
         with torch.no_grad():
             self.bias.zero_()
 
-    def forward(self, x, edge_index, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=True):
+    def forward(self, x, edge_index, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=None, correct=False):
         view = ops.as_view(edge_index, x.size(0))
         if x.dtype != ops.BF16:
             x = ops.mask_cast(x.float())[0]
+        out_fp32 = (not relu) if out_fp32 is None else out_fp32
         return ops.gat_layer(x, self.lin.weight, self.att_src, self.att_dst, self.bias, view, self.heads, self.negative_slope,
-                             relu, drop_p, drop_seed, drop_keep, out_fp32)
+                             relu, drop_p, drop_seed, drop_keep, out_fp32, correct)
 
 
 class GCNEncoder(nn.Module):
@@ -104,13 +107,14 @@ class GCNEncoder(nn.Module):
         view = ops.as_view(edge_index, x.size(0))
         if x.dtype != ops.BF16:
             x = ops.mask_cast(x.float())[0]
-        for layer in self.graph_layers[:-1]:
+        for i, layer in enumerate(self.graph_layers[:-1]):
             p, seed, keep = 0.0, 0, None
             if self.drop_out and self.training:
                 p = 0.2
-                seed, keep = self.draws.dropout((x.size(0), layer.out_channels), p, x.device)
-            x = layer(x, view, relu=True, drop_p=p, drop_seed=seed, drop_keep=keep, out_fp32=False)
-        return self.graph_layers[-1](x, view, relu=False, out_fp32=True)
+                seed, keep = self.draws.dropout((x.size(0), layer.heads * layer.out_channels if hasattr(layer, "heads") else layer.out_channels), p, x.device)
+            # layers fed by an activation (i > 0) restore the common-mode part of the weight rounding in fp32 (ops._xw)
+            x = layer(x, view, relu=True, drop_p=p, drop_seed=seed, drop_keep=keep, out_fp32=False, correct=i > 0)
+        return self.graph_layers[-1](x, view, relu=False, out_fp32=True, correct=len(self.graph_layers) > 1)
 
 
 class GATEncoder(GCNEncoder):

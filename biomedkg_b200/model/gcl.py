@@ -38,8 +38,8 @@ class GRACE(nn.Module):
         return z, z1, z2
 
     def project(self, z: torch.Tensor) -> torch.Tensor:
-        h = F.elu(ops.linear(z, self.fc1.weight, self.fc1.bias))
-        return ops.linear(h, self.fc2.weight, self.fc2.bias)
+        h = F.elu(ops.centered_linear(z, self.fc1.weight, self.fc1.bias))
+        return ops.centered_linear(h, self.fc2.weight, self.fc2.bias)
 
 
 class DGI(nn.Module):

@@ -332,6 +332,61 @@ def linear(x, weight, bias=None, out_bf16=False):
     return y.reshape(*lead, weight.shape[0])
 
 
+class _CenteredLinearFn(torch.autograd.Function):
+    """y = x W^T + b for fp32 x whose rows share a large common component (encoder outputs, projector activations):
+    x = 1 m^T + (x - 1 m^T) with m the column mean, so  y = bf16(x - m) bf16(W)^T  [tensor cores, fp32 accumulate]
+    + (W m + b)  [fp32, exact weights].  bf16 rounding then acts on the deviations only - with near-collapsed embeddings the
+    plain bf16 cast of x would erase exactly the part the contrastive gradient depends on (DESIGN.md "Centred bf16 operands")."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _need_cuda(x)
+        x = x.contiguous().float()
+        N, K = x.shape
+        m = colsum(x) / N
+        xc16 = torch.empty(N, K, dtype=BF16, device=x.device)
+        call("bmkg_center_cast", _p(x), _p(m), N, K, _p(xc16), _stream())
+        w16 = weight.to(BF16)
+        shift = torch.mv(weight.float(), m)
+        if bias is not None:
+            shift = shift + bias
+        y = _mm_f32(xc16, w16.t()) + shift
+        ctx.save_for_backward(xc16, w16, m)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xc16, w16, m = ctx.saved_tensors
+        g = g.contiguous()
+        g16 = g if g.dtype == BF16 else g.to(BF16)
+        db = _colsum_any(g)
+        dx = _mm_f32(g16, w16) if ctx.needs_input_grad[0] else None      # fp32 out: its column sums (bias gradients upstream) cancel heavily
+        dw = torch.addmm(_mm_f32(g16.t(), xc16), db.unsqueeze(1), m.unsqueeze(0)) if ctx.needs_input_grad[1] else None   # g^T (xc + 1 m^T)
+        return dx, dw, (db if ctx.has_bias and ctx.needs_input_grad[2] else None)
+
+
+def centered_linear(x, weight, bias=None):
+    if x.numel() % 4 or x.shape[-1] % 4:
+        return linear(x, weight, bias)
+    return _CenteredLinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+
+
+#: add the rank-1 fp32 correction  mean(x) (W - bf16(W))^T  to the conv layers' X W^T (False only for A/B numerics tests)
+WEIGHT_RESIDUAL = True
+
+
+def _xw(x16, weight, w16, correct):
+    """X W^T on the tensor cores with bf16 operands.  ``correct``: the layer input is an activation whose rows share a common
+    component m = colmean(x); the rounding of W then shifts every output row by the same vector m (W - bf16 W)^T, which is
+    restored in fp32 through the GEMM's bias epilogue (one [K] column mean + one [C,K] GEMV)."""
+    if not (correct and WEIGHT_RESIDUAL) or x16.size(1) % 8:
+        return torch.mm(x16, w16.t())
+    m = colsum_bf16(x16)[0] / x16.size(0)
+    dc = torch.mv(weight.detach().float() - w16.float(), m)
+    return torch.addmm(dc.to(BF16), x16, w16.t())
+
+
 # ---------------------------------------------------------------------------
 # GCN layer
 # ---------------------------------------------------------------------------
@@ -341,12 +396,14 @@ class _GCNLayerFn(torch.autograd.Function):
     aggregation kernel on the CSC, and two GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32):
+    def forward(ctx, x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32, correct=False):
         _need_cuda(x)
         assert x.dtype == BF16
+        if relu and out_fp32:
+            raise ValueError("relu=True needs out_fp32=False: the ReLU/dropout backward re-reads the saved bf16 output")
         x = x.contiguous()
         w16 = weight.to(BF16)
-        xw = torch.mm(x, w16.t())
+        xw = _xw(x, weight, w16, correct)
         y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
                           hub_rows=view.hub_csr if view.hub_possible else None)
         ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
@@ -372,11 +429,11 @@ class _GCNLayerFn(torch.autograd.Function):
         dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub_csc if view.hub_possible else None)
         dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
-        return dx, dw, dbias, None, None, None, None, None, None
+        return dx, dw, dbias, None, None, None, None, None, None, None
 
 
-def gcn_layer(x, weight, bias, view, relu, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False):
-    return _GCNLayerFn.apply(x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32)
+def gcn_layer(x, weight, bias, view, relu, drop_p=0.0, drop_seed=0, drop_keep=None, out_fp32=False, correct=False):
+    return _GCNLayerFn.apply(x, weight, bias, view, relu, drop_p, drop_seed, drop_keep, out_fp32, correct)
 
 
 # ---------------------------------------------------------------------------
@@ -387,16 +444,19 @@ class _GATLayerFn(torch.autograd.Function):
     Backward recomputes alpha from node arrays: a CSR pass (d a_dst, t) and a CSC pass (d xh, d a_src)."""
 
     @staticmethod
-    def forward(ctx, x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32):
+    def forward(ctx, x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32,
+                correct=False):
         _need_cuda(x)
         assert x.dtype == BF16
+        if relu and out_fp32:
+            raise ValueError("relu=True needs out_fp32=False: the ReLU/dropout backward re-reads the saved bf16 output")
         x = x.contiguous()
         N = x.size(0)
         HC = weight.size(0)
         C = HC // heads
         dev = x.device
         w16 = weight.to(BF16)
-        xh = torch.mm(x, w16.t())
+        xh = _xw(x, weight, w16, correct)
         atts = att_src.detach().reshape(-1).float().contiguous()
         attd = att_dst.detach().reshape(-1).float().contiguous()
         a_s = torch.empty(N, heads, dtype=torch.float32, device=dev)
@@ -448,12 +508,13 @@ class _GATLayerFn(torch.autograd.Function):
         datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
         dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None
         dx = torch.mm(dxh, w16) if ctx.needs_input_grad[0] else None
-        return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None
+        return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None, None
 
 
 def gat_layer(x, weight, att_src, att_dst, bias, view, heads=1, slope=0.2, relu=False, drop_p=0.0, drop_seed=0, drop_keep=None,
-              out_fp32=False):
-    return _GATLayerFn.apply(x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32)
+              out_fp32=False, correct=False):
+    return _GATLayerFn.apply(x, weight, att_src, att_dst, bias, view, heads, slope, relu, drop_p, drop_seed, drop_keep, out_fp32,
+                             correct)
 
 
 # ---------------------------------------------------------------------------
@@ -624,25 +685,34 @@ class _InfoNCEFn(torch.autograd.Function):
         N, D = h1.shape
         dev = h1.device
         scale = math.sqrt(LOG2E / tau)
+        rp = int(lib.bmkg_infonce_padded_rows(N, N))
         z = torch.empty(2 * N, D, dtype=BF16, device=dev)
+        a = torch.zeros(rp, dtype=torch.float32, device=dev)
         inv_norm = torch.empty(2 * N, dtype=torch.float32, device=dev)
-        call("bmkg_l2norm_scale", _p(h1), N, D, scale, _p(z), _p(inv_norm), _stream())
-        call("bmkg_l2norm_scale", _p(h2), N, D, scale, z.data_ptr() + N * D * 2, inv_norm.data_ptr() + N * 4, _stream())
+        cs = torch.empty(2, D, dtype=torch.float32, device=dev)
+        ws = _ws(lib.bmkg_colsum_workspace_bytes(N, D), dev)
+        call("bmkg_l2norm_colsum", _p(h1), N, D, _p(inv_norm), _p(cs[0]), _p(ws), ws.numel(), _stream())
+        call("bmkg_l2norm_colsum", _p(h2), N, D, inv_norm.data_ptr() + N * 4, _p(cs[1]), _p(ws), ws.numel(), _stream())
+        # common vector of the centred representation z_u = mu + d_u: the column mean of the normalised, scaled rows
+        mu = cs.sum(0) * (scale / (2.0 * N)) if CENTER_INFONCE else torch.zeros(D, dtype=torch.float32, device=dev)
+        call("bmkg_center_scale", _p(h1), _p(inv_norm), _p(mu), N, D, scale, _p(z), _p(a), _stream())
+        call("bmkg_center_scale", _p(h2), inv_norm.data_ptr() + N * 4, _p(mu), N, D, scale, z.data_ptr() + N * D * 2,
+             a.data_ptr() + N * 4, _stream())
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        inv_r = torch.empty(lib.bmkg_infonce_padded_rows(N), dtype=torch.float32, device=dev)
+        qw = torch.empty(rp, 2, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
-        call("bmkg_infonce_fwd", _p(z), N, D, _p(loss), _p(inv_r), _p(ws), ws.numel(), _stream())
-        ctx.save_for_backward(h1, h2, z, inv_norm, inv_r)
+        call("bmkg_infonce_fwd", _p(z), _p(a), N, D, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(h1, h2, z, inv_norm, qw, mu)
         ctx.scale = scale
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        h1, h2, z, inv_norm, inv_r = ctx.saved_tensors
+        h1, h2, z, inv_norm, qw, mu = ctx.saved_tensors
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        call("bmkg_infonce_bwd", _p(z), _p(inv_r), _p(g), N, D, _p(dz), _stream())
+        call("bmkg_infonce_bwd", _p(z), _p(qw), _p(mu), _p(g), N, D, _p(dz), _stream())
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())
         call("bmkg_l2norm_scale_bwd", _p(h2), inv_norm.data_ptr() + N * 4, dz.data_ptr() + N * D * 4, N, D, ctx.scale, _p(dh2),
@@ -650,16 +720,27 @@ class _InfoNCEFn(torch.autograd.Function):
         return dh1, dh2, None
 
 
-def infonce_loss(h1, h2, tau=0.2):
+#: centre the InfoNCE operand on its column mean (False = plain bf16 rows, mu = 0; only for A/B numerics tests)
+CENTER_INFONCE = True
+
+
+def pad_infonce_dim(h1, h2):
+    """Validate the projector width and zero-pad it to the 64-column K panels of the tcgen05 kernels (zero columns change
+    neither the norms nor the dot products).  Shared by the single-GPU and the row-sharded loss."""
     if h1.shape != h2.shape or h1.dim() != 2:
         raise ValueError("h1 and h2 must both be [N, D]")
     D = h1.size(1)
     if D > 256:
         raise ValueError("the fused InfoNCE kernels hold one 128 x D row block on chip: D <= 256 (reference default 256)")
-    if D % 64:   # the tcgen05 K loop works on 64-column panels: zero columns change neither the norms nor the dot products
+    if D % 64:
         pad = 64 - D % 64
         h1 = torch.nn.functional.pad(h1, (0, pad))
         h2 = torch.nn.functional.pad(h2, (0, pad))
+    return h1, h2
+
+
+def infonce_loss(h1, h2, tau=0.2):
+    h1, h2 = pad_infonce_dim(h1, h2)
     return _InfoNCEFn.apply(h1, h2, float(tau))
 
 

@@ -73,6 +73,61 @@ def infonce_l2l_closed_form(h1: torch.Tensor, h2: torch.Tensor, tau: float = 0.2
     return -(2.0 * d - torch.log(r1) - torch.log(r2)).sum() / (2.0 * n)
 
 
+class _InfoNCEBlockwise(torch.autograd.Function):
+    """The closed form above evaluated in row blocks of the stacked 2N x 2N similarity matrix, with a hand-written backward,
+    so full-size configurations (N = 28k: the dense fp64 form needs ~40 GB) run in a few GB.  Optional hooks let
+    oracle/emu.py round the operand / the probabilities exactly where the CUDA kernels do; with no hooks this is the
+    plain fp64/fp32 closed form (tests/test_oracle.py checks it against infonce_l2l_closed_form and the as-written form)."""
+
+    @staticmethod
+    def forward(ctx, h1, h2, tau, block, z_hook, p_hook):
+        n = h1.size(0)
+        h = torch.cat([h1, h2], 0)
+        inv = 1.0 / h.norm(dim=1).clamp_min(1e-12)          # F.normalize eps
+        z = h * inv.unsqueeze(1)                              # unit rows
+        mu = torch.zeros_like(z[0])
+        if z_hook is not None:
+            z, mu = z_hook(z)                                  # (deviations-or-rows used in products, common vector)
+        zz = z + mu                                            # the represented rows
+        R = torch.empty(2 * n, dtype=h.dtype)
+        for b0 in range(0, 2 * n, block):
+            e = torch.exp((zz[b0:b0 + block] @ zz.t()) / tau)
+            idx = torch.arange(b0, min(b0 + block, 2 * n))
+            e[idx - b0, idx] = 0.0
+            R[b0:b0 + block] = e.sum(1)
+        pos = (zz[:n] * zz[n:]).sum() / tau
+        loss = (torch.log(R).sum() - 2.0 * pos) / (2.0 * n)
+        ctx.save_for_backward(h, inv, z, mu, R)
+        ctx.meta = (n, tau, block, p_hook)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        h, inv, z, mu, R = ctx.saved_tensors
+        n, tau, block, p_hook = ctx.meta
+        zz = z + mu
+        ir = 1.0 / R
+        dzz = torch.empty_like(zz)
+        for b0 in range(0, 2 * n, block):
+            e = torch.exp((zz[b0:b0 + block] @ zz.t()) / tau)
+            idx = torch.arange(b0, min(b0 + block, 2 * n))
+            e[idx - b0, idx] = 0.0
+            P = e * (ir[b0:b0 + block].unsqueeze(1) + ir.unsqueeze(0))
+            Pr = p_hook(P) if p_hook is not None else P
+            # rounded probabilities multiply the deviation part only; the common vector rides on the exact row sums
+            dzz[b0:b0 + block] = Pr @ z + P.sum(1, keepdim=True) * mu
+        pair = torch.cat([zz[n:], zz[:n]], 0)
+        dzz = (g / (2.0 * n * tau)) * (dzz - 2.0 * pair)
+        u = h * inv.unsqueeze(1)
+        dh = inv.unsqueeze(1) * (dzz - u * (u * dzz).sum(1, keepdim=True))
+        return dh[:n], dh[n:], None, None, None, None
+
+
+def infonce_l2l_blockwise(h1, h2, tau: float = 0.2, block: int = 2048, z_hook=None, p_hook=None):
+    """infonce_l2l_closed_form in O(block x 2N) memory (see _InfoNCEBlockwise)."""
+    return _InfoNCEBlockwise.apply(h1, h2, tau, block, z_hook, p_hook)
+
+
 class DualBranchContrast(torch.nn.Module):
     """Oracle stand-in for GCL.models.DualBranchContrast (L2L only, as used)."""
 

@@ -33,14 +33,15 @@ def test_python_binding_covers_header(libpath):
     from biomedkg_b200 import _cabi
 
     assert sorted(_cabi.SIGNATURES) == _declared()
-    assert _cabi.lib.bmkg_abi_version() == 1
+    assert _cabi.lib.bmkg_abi_version() == 2
     assert b"workspace" in _cabi.lib.bmkg_error_string(-3)
 
 
 def test_host_side_size_queries(libpath):
     from biomedkg_b200._cabi import lib
 
-    assert lib.bmkg_infonce_padded_rows(100) == 256 and lib.bmkg_infonce_padded_rows(64) == 128
+    assert lib.bmkg_infonce_padded_rows(100, 100) == 256 and lib.bmkg_infonce_padded_rows(64, 64) == 128
+    assert lib.bmkg_infonce_stacked_rows(1000, 384) == 2304 and lib.bmkg_infonce_padded_rows(1000, 384) == 2304
     assert lib.bmkg_edge_sort_workspace_bytes(1000, 50_000) >= 50_000 * 24
     assert lib.bmkg_csr_filter_workspace_bytes(1000, 50_000) >= 50_000 * 8
     assert lib.bmkg_infonce_workspace_bytes(8000, 256) > 0
@@ -135,7 +136,7 @@ def test_header_is_plain_c_and_links(libpath, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "cabi.c"
     src.write_text('#include "bmkg_b200.h"\n#include <stdio.h>\n'
-                   'int main(void) { printf("%d %lld\\n", bmkg_abi_version(), (long long)bmkg_infonce_padded_rows(100)); return 0; }\n')
+                   'int main(void) { printf("%d %lld\\n", bmkg_abi_version(), (long long)bmkg_infonce_padded_rows(100, 100)); return 0; }\n')
     exe = tmp_path / "cabi"
     libdir = os.path.dirname(libpath)
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", str(src), "-I", os.path.join(root, "include"), "-L", libdir,

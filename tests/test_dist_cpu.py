@@ -13,61 +13,83 @@ import torch.multiprocessing as mp
 from oracle import pygcl
 
 
-def test_row_partition_properties():
-    from biomedkg_b200.dist import row_partition
+def test_shard_layout_properties():
+    from biomedkg_b200.dist import shard_layout
 
-    for rows in (10, 128, 129, 1000, 56_000, 2_000_000):
+    for n in (10, 128, 129, 1000, 28_000, 130_000, 1_000_000):
         for world in (1, 2, 3, 4, 8):
-            parts = row_partition(rows, world)
-            assert parts[0][0] == 0 and parts[-1][1] == rows
+            B, parts = shard_layout(n, world)
+            assert B % 128 == 0 and B * world >= n
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            for p, (b0, e0) in enumerate(parts):
+                assert b0 == min(p * B, n) and b0 <= e0 <= b0 + B
             for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
-                assert e0 == b1 and b0 <= e0
-            assert all(b % 128 == 0 for b, _ in parts)
-            sizes = [e - b for b, e in parts]
-            assert max(sizes) - min(sizes) <= 128 + 127
+                assert e0 == b1
+
+
+def _node_of_row(u, B):
+    blk = u // B
+    return (blk // 2) * B + (u - blk * B), blk % 2
 
 
 class TorchRowImpl:
-    """fp64 torch restatement of what the row-range kernels compute (same scaling convention, exact exp2)."""
+    """fp64 torch restatement of what the row-range kernels compute on the block-interleaved stacked layout of
+    include/bmkg_b200.h (centred operand z_u = mu + d_u, q_u = 1/R'_u, w_u = 2^a_u; exact exp2, no bf16 rounding)."""
 
-    def prep(self, h1, h2, tau):
-        scale = math.sqrt(1.4426950408889634 / tau)
-        z = torch.cat([torch.nn.functional.normalize(h1.double()), torch.nn.functional.normalize(h2.double())]) * scale
-        inv_norm = torch.cat([1 / h1.double().norm(dim=1), 1 / h2.double().norm(dim=1)])
-        return z, inv_norm, scale
+    def stats(self, h):
+        inv = 1 / h.double().norm(dim=1).clamp_min(1e-12)
+        return inv, (h.double() * inv[:, None]).sum(0)
 
-    def fwd_rows(self, z, N, r0, r1):
-        inv_r = torch.zeros(((2 * N + 127) // 128) * 128, dtype=torch.float32)
-        loss = torch.zeros((), dtype=torch.float32)
+    def center(self, hs, invs, mu, B, scale):
+        D = hs[0].size(1)
+        z = torch.zeros(2, B, D, dtype=torch.float64)
+        a = torch.zeros(2, B, dtype=torch.float64)
+        for v, (h, inv) in enumerate(zip(hs, invs)):
+            n = h.size(0)
+            z[v, :n] = h.double() * inv[:, None] * scale - mu
+            a[v, :n] = z[v, :n] @ mu
+        return z, a
+
+    def _valid(self, R_all, N, B):
+        u = torch.arange(R_all)
+        node, view = _node_of_row(u, B)
+        return node < N, view
+
+    def fwd_rows(self, Z, A, N, B, r0, r1):
+        R_all = Z.size(0)
+        qw = torch.zeros(R_all, 2, dtype=torch.float64)
+        loss = torch.zeros((), dtype=torch.float64)
         if r1 > r0:
-            S = torch.exp2(z[r0:r1] @ z.t())
-            S[torch.arange(r1 - r0), torch.arange(r0, r1)] = 0
-            R = S.sum(1)
-            inv_r[r0:r1] = (1 / R).float()
-            u = torch.arange(r0, r1)
-            pos = u[u < N]
-            dots = (z[pos] * z[pos + N]).sum(1)
-            loss = ((R.log().sum() - 2 * math.log(2.0) * dots.sum()) / (2 * N)).float()
-        return loss, inv_r
+            valid, view = self._valid(R_all, N, B)
+            E = torch.exp2(Z[r0:r1] @ Z.t() + A[None, :]) * valid[None, :]
+            E[torch.arange(r1 - r0), torch.arange(r0, r1)] = 0
+            Rp = E.sum(1)
+            rows = torch.arange(r0, r1)
+            ok = valid[r0:r1]
+            qw[rows[ok], 0] = 1 / Rp[ok]
+            qw[rows[ok], 1] = torch.exp2(A[rows[ok]])
+            first = rows[ok & (view[r0:r1] == 0)]
+            dots = (Z[first] * Z[first + B]).sum(1)
+            loss = (Rp[ok].log().sum() - math.log(2.0) * A[rows[ok]].sum() - 2 * math.log(2.0) * dots.sum()) / (2 * N)
+        return loss, qw
 
-    def bwd_rows(self, z, inv_r, g, N, r0, r1):
-        dz = torch.zeros(2 * N, z.size(1), dtype=torch.float32)
+    def bwd_rows(self, Z, QW, mu, g, N, B, r0, r1):
+        dz = torch.zeros(max(r1 - r0, 1), Z.size(1), dtype=torch.float64)
         if r1 > r0:
-            c = inv_r[: 2 * N].double()
-            P = torch.exp2(z[r0:r1] @ z.t()) * (c[r0:r1, None] + c[None, :])
+            q, w = QW[:, 0], QW[:, 1]
+            P = torch.exp2(Z[r0:r1] @ Z.t()) * (q[r0:r1, None] * w[None, :] + q[None, :] * w[r0:r1, None])
             P[torch.arange(r1 - r0), torch.arange(r0, r1)] = 0
-            pair = torch.cat([torch.arange(N, 2 * N), torch.arange(0, N)])[r0:r1]
-            dz[r0:r1] = (float(g) * math.log(2.0) / (2 * N) * (P @ z - 2 * z[pair])).float()
+            rows = torch.arange(r0, r1)
+            node, view = _node_of_row(rows, B)
+            pair = torch.where(view == 0, rows + B, rows - B)
+            out = float(g) * math.log(2.0) / (2 * N) * (P @ Z + (P.sum(1, keepdim=True) - 2.0) * mu[None, :] - 2 * Z[pair])
+            dz[: r1 - r0] = out * (node < N)[:, None]
         return dz
 
-    def norm_bwd(self, h1, h2, inv_norm, dz, scale):
-        out = []
-        N = h1.size(0)
-        for h, inv, d in ((h1, inv_norm[:N], dz[:N]), (h2, inv_norm[N:], dz[N:])):
-            u = h.double() * inv[:, None]
-            d = d.double()
-            out.append((scale * inv[:, None] * (d - u * (u * d).sum(1, keepdim=True))).to(h.dtype))
-        return out
+    def norm_bwd(self, h, inv, dz, scale):
+        u = h.double() * inv[:, None]
+        d = dz.double()
+        return (scale * inv[:, None] * (d - u * (u * d).sum(1, keepdim=True))).to(h.dtype)
 
 
 def _free_port():
@@ -76,37 +98,49 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, d, out):
+def _worker(rank, world, port, n, d, out, replicated):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from biomedkg_b200.dist import _ShardedInfoNCEFn
+        from biomedkg_b200.dist import shard_layout, sharded_infonce_local, sharded_infonce_loss
 
         g = torch.Generator().manual_seed(5)           # identical (replicated) inputs on every rank
-        h1 = torch.randn(n, d, generator=g, requires_grad=True)
-        h2 = (h1.detach() + torch.randn(n, d, generator=g)).requires_grad_(True)
-        loss = _ShardedInfoNCEFn.apply(h1, h2, 0.2, None, TorchRowImpl())
-        (loss * 3.0).backward()                        # non-trivial upstream gradient
-        out[rank] = (float(loss), h1.grad.clone(), h2.grad.clone())
+        h1 = torch.randn(n, d, generator=g, dtype=torch.float64)
+        h2 = h1 + torch.randn(n, d, generator=g, dtype=torch.float64)
+        if replicated:                                  # replicated encoder: full tensors in, full gradients out
+            h1.requires_grad_(True), h2.requires_grad_(True)
+            loss = sharded_infonce_loss(h1, h2, 0.2, None, TorchRowImpl())
+            (loss * 3.0).backward()                    # non-trivial upstream gradient
+            out[rank] = (float(loss), h1.grad.clone(), h2.grad.clone(), (0, n))
+        else:                                           # row-sharded encoder: every rank holds only its node block
+            B, parts = shard_layout(n, world)
+            n0, n1 = parts[rank]
+            a, b = h1[n0:n1].clone().requires_grad_(True), h2[n0:n1].clone().requires_grad_(True)
+            loss = sharded_infonce_local(a, b, n, 0.2, None, TorchRowImpl())
+            (loss * 3.0).backward()
+            out[rank] = (float(loss), a.grad.clone(), b.grad.clone(), (n0, n1))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,d,world", [(200, 64, 2), (129, 32, 2), (64, 32, 2)])
-def test_sharded_infonce_matches_single_process_oracle(n, d, world):
+@pytest.mark.parametrize("replicated", [False, True])
+@pytest.mark.parametrize("n,d,world", [(300, 64, 2), (129, 32, 2), (64, 32, 2)])
+def test_sharded_infonce_matches_single_process_oracle(n, d, world, replicated):
+    """(64, 32, 2): B = 128 > N, so rank 1 owns no rows at all - the collectives must still line up."""
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), n, d, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, d, out, replicated), nprocs=world, join=True)
     g = torch.Generator().manual_seed(5)
-    h1 = torch.randn(n, d, generator=g).double().requires_grad_(True)
-    h2 = (h1.detach() + torch.randn(n, d, generator=g).double()).requires_grad_(True)
+    h1 = torch.randn(n, d, generator=g, dtype=torch.float64)
+    h2 = (h1 + torch.randn(n, d, generator=g, dtype=torch.float64)).requires_grad_(True)
+    h1.requires_grad_(True)
     ref = pygcl.infonce_l2l_as_written(h1, h2, 0.2, True)
     (ref * 3.0).backward()
     for r in range(world):
-        loss, g1, g2 = out[r]
-        assert abs(loss - float(ref)) < 1e-5 * abs(float(ref))
-        assert torch.allclose(g1.double(), h1.grad, rtol=1e-4, atol=1e-7)
-        assert torch.allclose(g2.double(), h2.grad, rtol=1e-4, atol=1e-7)
+        loss, g1, g2, (n0, n1) = out[r]
+        assert abs(loss - float(ref)) < 1e-9 * abs(float(ref))
+        assert torch.allclose(g1, h1.grad[n0:n1], rtol=1e-7, atol=1e-12)
+        assert torch.allclose(g2, h2.grad[n0:n1], rtol=1e-7, atol=1e-12)
     assert out[0][0] == out[1][0]                      # every rank ends with the same loss
 
 
