@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py - GCL nodes/s of one full-graph GRACE training step (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4] [--impl ours|reference] [--mode rowshard|dp]
 
 A "step" = fusion + 3 encoder passes + projector + InfoNCE + backward + grad all-reduce (N>1) + grad clip + Adam,
-exactly BaseGCL.training_step + the Lightning optimiser step of the reference (gcl_module.py:60-64,
-train_gcl.py:99).  N=1 workload: BASELINE.json configs[1] (GRACE + GAT + attention fusion of 2 modalities,
-~28k nodes / ~650k edges).  N>1: every rank runs its own subgraph of that shape (the reference's DDP regime:
-per-rank contrast, gradients all-reduced over NCCL) -> weak scaling, value = total nodes / max-over-ranks time.
+exactly BaseGCL.training_step + the Lightning optimiser step of the reference (gcl_module.py:60-64, train_gcl.py:99).
+
+Workload (every N): BASELINE.json configs[3], the PrimeKG++-scale full graph (130k nodes, 8M edges, 3-modality attention
+fusion, GRACE + GCN).  N=1 runs it on one GPU; N>1 runs THE SAME graph row-sharded over the N ranks (nodes partitioned by
+destination row, layer inputs / InfoNCE operand all-gathered over NVLink, parameter gradients all-reduced - the north star's
+partition) -> strong scaling, value = nodes / max-over-ranks step time.  ``--mode dp`` keeps the reference's own DDP regime
+(every rank its own graph, weak scaling) as an option.  At N=1 the line also carries, under "also", the device-resident
+nodes/s of cfg2 (GAT + attention, CUDA-graph replay) and cfg1, and under roofline.also the CSR aggregation at cfg5 size.
 
 Prints ONE JSON line (see the driver contract in DESIGN.md "Measurement").
 """
@@ -27,7 +31,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 CONFIGS = {
-    # name: (N, E, M, fuse, encoder, objective)  - BASELINE.json configs, SURVEY.md section 8 table
+    # BASELINE.json configs, SURVEY.md section 8 table
     "cfg1": dict(N=8_000, E=2_670_000, M=1, fuse="none", encoder="gcn", desc="GRACE + 2-layer-hidden GCN, drug subgraph"),
     "cfg2": dict(N=28_000, E=650_000, M=2, fuse="attention", encoder="gat", desc="GRACE + GAT + attention fusion (2 modalities), gene/protein subgraph"),
     "cfg4": dict(N=130_000, E=8_000_000, M=3, fuse="attention", encoder="gcn", desc="PrimeKG++-scale full graph, 3-modality fusion, GRACE"),
@@ -57,6 +61,24 @@ def synth(cfg, seed, pin=False):
     if pin:
         x, ei = x.pin_memory(), ei.pin_memory()
     return x, ei
+
+
+def config_dict(name, world, mode):
+    """The ``config`` object of the JSON line - shared by both arms so the driver compares like with like."""
+    cfg = CONFIGS[name]
+    if world == 1:
+        par = "single GPU"
+    elif mode == "rowshard":
+        par = (f"rowshard{world}: ONE graph, nodes partitioned by destination row over {world} ranks (fusion / GEMMs / aggregation / projector "
+               f"on the rank's rows, NCCL all-gather of layer inputs and of the InfoNCE operand, InfoNCE rows of the rank's own nodes, "
+               f"parameter gradients all-reduced)" if cfg["encoder"] == "gcn" else
+               f"rowshard{world}: ONE graph, replicated GAT encoder, InfoNCE rows split over {world} ranks")
+    else:
+        par = f"dp{world}: every rank its own graph, NCCL gradient all-reduce (the reference's DDP regime)"
+    return {"workload": f"{name}: {cfg['desc']}", "nodes": cfg["N"] * (world if mode == "dp" else 1), "edges": cfg["E"] * (world if mode == "dp" else 1),
+            "modalities": cfg["M"], "fuse": cfg["fuse"], "encoder": cfg["encoder"], "objective": "GRACE (InfoNCE L2L, intraview negatives, tau 0.2)",
+            "in_dim": IN_DIM, "hidden": HID, "conv_layers": LAYERS + 2, "parallelism": par,
+            "unused_view": "computed (faithful to model/gcl.py:44)"}
 
 
 class ClockSampler:
@@ -95,16 +117,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: the restated PyG/PyGCL path ("as written"), timed on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(cfg, n_sample, steps, warmup, seed=42):
+def cpu_reference_step_rate(cfg, n_nodes, steps, warmup, seed=42):
     """nodes/s of the oracle's as-written GRACE step (COO gather + scatter_add_, mask-materialising [N,2N] InfoNCE -
-    the operations PyG 2.5.3 / PyGCL 0.1.2 execute) on a bounded sample: an n_sample-node graph of the same shape
-    (same average degree, modalities, encoder, objective).  fp32, all host threads."""
+    the operations PyG 2.5.3 / PyGCL 0.1.2 execute).  n_nodes == cfg["N"]: the configuration in full; smaller: a bounded
+    sample, an n_nodes-node graph of the same shape (same average degree, modalities, encoder, objective).  fp32, all host threads."""
     from oracle import models as om
 
     torch.set_num_threads(os.cpu_count() or 1)
     sub = dict(cfg)
-    sub["N"] = n_sample
-    sub["E"] = max(1, int(cfg["E"] * n_sample / cfg["N"]))
+    sub["N"] = n_nodes
+    sub["E"] = max(1, int(cfg["E"] * n_nodes / cfg["N"]))
     x, ei = synth(sub, seed)
     torch.manual_seed(seed)
     mod = om.GRACEModule(IN_DIM, HID, HID, LAYERS, fuse_method=cfg["fuse"], encoder=cfg["encoder"]).train()
@@ -124,26 +146,59 @@ def cpu_reference_step_rate(cfg, n_sample, steps, warmup, seed=42):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return n_sample / dt, dt, sub
+    return n_nodes / dt, dt, sub
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:  # noqa: BLE001
+        pass
+    return 0.0
 
 
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (restated: PyG / PyGCL are not installable) on all host cores.
+    Headline: args.config with --steps / --warmup honoured, every step a bounded sample of the workload (the as-written
+    [N,2N] fp32 InfoNCE needs ~7 x 135 GB at cfg4's 130k nodes, it cannot run in full).  "also": the configurations the host
+    CAN run in full - cfg1 always, cfg2 when >= 100 GB of RAM are available - so that same-config pairs exist next to the
+    GPU arm's "also" entries."""
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    n_sample = args.cpu_sample_nodes
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    rate, dt, sub = cpu_reference_step_rate(cfg, n_sample, steps, warmup)
     cores = os.cpu_count() or 1
-    sample = (f"restated reference path (PyG/PyGCL not installable): oracle as-written GRACE step on a {sub['N']}-node / "
-              f"{sub['E']}-edge sample of {args.config} (same degree, M={cfg['M']}, fuse={cfg['fuse']}, encoder={cfg['encoder']}), "
-              f"fp32, {steps} steps")
+    n_sample = min(args.cpu_sample_nodes, cfg["N"])
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    rate, dt, sub = cpu_reference_step_rate(cfg, n_sample, steps, warmup)
+    sample = (f"restated reference path (PyG/PyGCL not installable): oracle as-written GRACE step, fp32, {cores} threads; each step a "
+              f"{sub['N']}-node / {sub['E']}-edge sample of {args.config} (same degree, M={cfg['M']}, fuse={cfg['fuse']}, encoder={cfg['encoder']}); "
+              f"{steps} steps after {warmup} warm-up, {dt:.2f} s/step.  The full configuration cannot run as written "
+              f"([N,2N] fp32 temporaries of {4 * 2 * cfg['N'] ** 2 / 1e9:.0f} GB each); per-node cost grows with N, so the sample favours the CPU")
+    also = {}
+    if not args.no_also:
+        t0 = time.time()
+        r1, d1, _ = cpu_reference_step_rate(CONFIGS["cfg1"], CONFIGS["cfg1"]["N"], 3, 1)
+        also["cfg1_full"] = {"value": r1, "unit": "nodes/s", "s_per_step": d1, "steps": 3, "warmup": 1, "nodes": CONFIGS["cfg1"]["N"],
+                             "edges": CONFIGS["cfg1"]["E"], "same_config_as": "also.cfg1 of the GPU arm"}
+        avail = _mem_available_gb()
+        if avail >= 100.0 and time.time() - t0 < 120:
+            try:
+                r2, d2, _ = cpu_reference_step_rate(CONFIGS["cfg2"], CONFIGS["cfg2"]["N"], 1, 0)
+                also["cfg2_full"] = {"value": r2, "unit": "nodes/s", "s_per_step": d2, "steps": 1, "warmup": 0, "nodes": CONFIGS["cfg2"]["N"],
+                                     "edges": CONFIGS["cfg2"]["E"], "same_config_as": "also.cfg2 of the GPU arm"}
+            except (RuntimeError, MemoryError) as exc:
+                also["cfg2_full"] = {"unavailable": f"reference OOM ({type(exc).__name__})"}
+        else:
+            also["cfg2_full"] = {"unavailable": f"reference OOM: the as-written loss needs ~45-90 GB, MemAvailable = {avail:.0f} GB"}
     line = {
         "impl": "reference", "metric": "GCL nodes/sec", "value": rate, "unit": "nodes/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.config}: {cfg['desc']}", "sample_nodes": sub["N"], "sample_edges": sub["E"]},
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.mode == "rowshard" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.config, max(1, args.gpus), args.mode),
         "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "also": also,
     }
     _emit(line)
 
@@ -151,10 +206,130 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Batch:
+    pass
+
+
+def _make_module(cfg, dev):
+    import biomedkg_b200 as b
+
+    torch.manual_seed(42)
+    return b.GRACEModule(IN_DIM, HID, HID, LAYERS, scheduler_type="cosine", learning_rate=1e-3, warm_up_ratio=0.2,
+                         fuse_method=cfg["fuse"], encoder=cfg["encoder"]).to(dev).train()
+
+
+def side_workload(name, dev, steps, warmup, use_graph=True):
+    """Device-resident nodes/s of another BASELINE configuration on this GPU (N=1 'also' entries): same step, same timing rules."""
+    from biomedkg_b200.graphed import GraphedStep
+
+    cfg = CONFIGS[name]
+    x_host, ei_host = synth(cfg, 42)
+    mod = _make_module(cfg, dev)
+    params = list(mod.model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    bt = Batch()
+    bt.x, bt.edge_index = x_host.to(dev), ei_host.to(dev)
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(bt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        eager()
+    run, graphed = eager, False
+    if use_graph:
+        try:
+            opt.zero_grad(set_to_none=True)
+            gs = GraphedStep(mod, bt.x, bt.edge_index, resort=False)
+
+            def run():
+                loss = gs()
+                torch.nn.utils.clip_grad_norm_(params, 1.0)
+                opt.step()
+                return loss
+
+            graphed = True
+            for _ in range(warmup):
+                run()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] {name}: CUDA-graph capture failed ({type(exc).__name__}: {exc}); eager", file=sys.stderr)
+            run = eager
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": cfg["N"] / (ms * 1e-3), "unit": "nodes/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "nodes": cfg["N"],
+           "edges": cfg["E"], "cuda_graph": graphed, "final_loss": float(loss.detach()), "workload": f"{name}: {cfg['desc']}"}
+    del mod, opt, bt
+    torch.cuda.empty_cache()
+    return out
+
+
+def aggregation_roofline(dev, peaks):
+    """bmkg_gcn_aggregate at BASELINE cfg5 size (1M nodes, 50M power-law edges, C=256, one 40%-dropped view): the honest HBM
+    test (512 MB of bf16 rows, far beyond L2).  Algorithmic bytes per SURVEY.md 8d: E'(C s + 4) + N C s + 4 (N + 1)."""
+    from biomedkg_b200 import ops
+
+    cfg = CONFIGS["cfg5"]
+    N, C = cfg["N"], HID
+    _, ei = synth(dict(cfg, M=1), 42)
+    ei = ei.to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    keep = torch.rand(ei.size(1), device=dev, generator=g) >= 0.4
+    sg = ops.sorted_graph(ei, N, cache=False)
+    view = sg.view(keep)
+    x = torch.randn(N, C, device=dev, generator=g).to(torch.bfloat16)
+    bias = torch.zeros(C, device=dev)
+    nnz = int(view.nnz.item())
+    hub = view.hub_csr if view.hub_possible else None
+
+    def call_fwd():
+        return ops.gcn_aggregate(view.rowptr, view.colind, view.dis, x, bias, True, 0.2, 1234, None, False, hub_rows=hub)
+
+    def call_bwd():
+        return ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, x, hub_rows=view.hub_csc if view.hub_possible else None)
+
+    out = {}
+    for name, fn in (("forward (CSR, fused norm+bias+ReLU+dropout)", call_fwd), ("transposed backward (CSC)", call_bwd)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        alg = nnz * (C * 2 + 4) + N * C * 2 + 4 * (N + 1)
+        gbs = alg / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": alg, "achieved_gbs": gbs, "frac_of_hbm": gbs / peaks.get("hbm_gbs", 6538.3)}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj.get("gcn_aggregate_kernel")
+    except Exception:  # noqa: BLE001
+        pass
+    res = {"kernel": "bmkg_gcn_aggregate", "bound": "hbm", "nodes": N, "edges_in_view_incl_self_loops": nnz, "channels": C,
+           "peak_gbs": peaks.get("hbm_gbs", 6538.3), "calls": out,
+           "ncu_dram_bytes": traffic or "profiles/r1_ncu_gcn_aggregate_N1M_E50M.txt: 14.2 GB per launch at 1M nodes / 31M kept edges (ER graph)",
+           "l2_policy": "10 back-to-back calls over 512 MB of rows + 250 MB of indices (> 126 MB L2)"}
+    del sg, view, x, ei, keep
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
-    import biomedkg_b200 as b
     from biomedkg_b200 import _cabi
 
     torch.cuda.set_device(local_rank)
@@ -162,12 +337,9 @@ def run_ours(args, rank, world, local_rank):
     cfg = CONFIGS[args.config]
     N, E, M = cfg["N"], cfg["E"], cfg["M"]
     rowshard = args.mode == "rowshard" and world > 1
-    # dp: every rank its own graph (weak scaling, the reference's DDP regime); rowshard: ONE graph on all ranks, the
-    # InfoNCE rows split over the ranks (strong scaling, full-graph loss - SURVEY.md 8e)
-    x_host, ei_host = synth(cfg, 42 if rowshard else 42 + rank, pin=True)
-    torch.manual_seed(42)
-    mod = b.GRACEModule(IN_DIM, HID, HID, LAYERS, scheduler_type="cosine", learning_rate=1e-3, warm_up_ratio=0.2,
-                        fuse_method=cfg["fuse"], encoder=cfg["encoder"]).to(dev).train()
+    # rowshard: ONE graph on all ranks (strong scaling, full-graph loss - SURVEY.md 8e); dp: every rank its own graph (weak)
+    x_host, ei_host = synth(cfg, 42 if (rowshard or world == 1) else 42 + rank, pin=True)
+    mod = _make_module(cfg, dev)
     full_shard = rowshard and cfg["encoder"] == "gcn"     # GCN: encoder rows sharded too; GAT: encoder replicated, InfoNCE sharded
     if rowshard and not full_shard:
         from biomedkg_b200.dist import ShardedDualBranchContrast
@@ -175,9 +347,6 @@ def run_ours(args, rank, world, local_rank):
         mod.contrast_model = ShardedDualBranchContrast(tau=TAU)
     params = [p for p in mod.model.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3)
-
-    class Batch:
-        pass
 
     use_graph = args.graph == "on" or (args.graph == "auto" and not rowshard)
     graphed = {}      # "resident" / "e2e" -> GraphedStep (captured lazily, after the eager warm-up)
@@ -240,6 +409,8 @@ def run_ours(args, rank, world, local_rank):
             print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
             use_graph = False
             torch.cuda.synchronize()
+    timed = {"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate_rows",
+             "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"}
     if use_graph:
         run = lambda bt: graph_step("resident", bt)  # noqa: E731
         for _ in range(args.warmup):
@@ -247,7 +418,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         # events cannot bracket kernels inside a replayed graph: per-kernel durations come from eager steps of the same
         # training step, run right here (same clocks, same data), not from the replayed region
-        _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_gcn_aggregate_rows", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+        _cabi.timed_entries.update(timed)
         _cabi.timings.clear()
         for _ in range(3):
             step(res)
@@ -261,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
             run(res)
         barrier()
     else:
-        _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate_rows", "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"})
+        _cabi.timed_entries.update(timed)
         _cabi.timings.clear()
     launches0 = _cabi.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,7 +456,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    nodes_total = N if rowshard else N * world
+    nodes_total = N if (rowshard or world == 1) else N * world
     value = nodes_total / (ms_max * 1e-3)
     final_loss = float(loss.detach())
 
@@ -298,9 +469,9 @@ def run_ours(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream(device=dev)
     x_src = x_host
     if full_shard:   # a sharded loader moves only this rank's node block of the features (edge_index stays replicated)
-        from biomedkg_b200.dist import node_partition
+        from biomedkg_b200.dist import shard_layout
 
-        b0, b1 = node_partition(N, world)[1][rank]
+        b0, b1 = shard_layout(N, world)[1][rank]
         x_src = x_host[b0:b1].contiguous().pin_memory()
 
     def prefetch():
@@ -352,9 +523,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": (x_src.numel() * 4 + ei_host.numel() * 8) * (world if rowshard else 1),
-           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
-           "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
+    h2d = x_src.numel() * 4 + ei_host.numel() * 8
+    ht = torch.tensor([float(h2d)], device=dev)
+    if world > 1:
+        dist.all_reduce(ht)                                  # bytes copied by all ranks per step
+    e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(ht.item()),
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms,
+           "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream; row-sharded ranks copy their own node block of "
+                   "x and the whole edge_index), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
                    + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if e2e_graph else "")}
 
     clocks = sampler.stop((wall0, wall1), (wall2, wall3)) if rank == 0 else None    # both timed regions (device-resident and end-to-end)
@@ -378,13 +554,18 @@ def run_ours(args, rank, world, local_rank):
         ach = flops_bwd / (kern_ms["bmkg_infonce_bwd"] * 1e-3) / 1e12
         traffic = None   # DRAM bytes per launch from the committed ncu --set full capture, only if it was taken at this N
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["infonce_bwd_kernel"]
-            if tj["N"] == N:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            for fn in ("r2_traffic.json", "r1_traffic.json"):
+                path = os.path.join(ROOT, "profiles", fn)
+                if os.path.exists(path):
+                    tj = json.load(open(path))["infonce_bwd_kernel"]
+                    if tj["N"] == N:
+                        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                        break
         except Exception:  # noqa: BLE001
             pass
         roof = {"kernel": "infonce_bwd_kernel (tcgen05)", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach / peak_tf, "traffic": traffic, "algorithmic_flops_per_launch": flops_bwd, "ms_per_launch": kern_ms["bmkg_infonce_bwd"],
+                "frac": ach / peak_tf, "traffic": traffic, "algorithmic_flops_per_launch": flops_bwd / (world if rowshard else 1),
+                "ms_per_launch": kern_ms["bmkg_infonce_bwd"] / (world if rowshard else 1),
                 "peak_source": peak_src,
                 # SURVEY 8(d) credits only the four dZ GEMMs (8N^2D); the kernel also recomputes S on the tensor pipe (another
                 # 8N^2D with the 2Nx2N Gram form), so the tcgen05 pipe itself runs at twice the credited rate
@@ -395,28 +576,42 @@ def run_ours(args, rank, world, local_rank):
                                                       "frac": (flops_fwd + flops_bwd) / ((kern_ms["bmkg_infonce_fwd"] + kern_ms["bmkg_infonce_bwd"]) * 1e-3) / 1e12 / peak_tf}}}
         agg_key = "bmkg_gat_aggregate" if cfg["encoder"] == "gat" else "bmkg_gcn_aggregate_rows"
         if agg_key in kern_ms:
-            roof["also"][agg_key] = {"ms_avg_per_call": kern_ms[agg_key], "calls_per_step": kern_calls[agg_key]}
+            roof["also"][agg_key + " (in-step, L2-resident rows at this size)"] = {"ms_avg_per_call": kern_ms[agg_key], "calls_per_step": kern_calls[agg_key]}
         if "bmkg_gat_aggregate_bwd" in kern_ms:
             roof["also"]["bmkg_gat_aggregate_bwd"] = {"ms_avg_per_call": kern_ms["bmkg_gat_aggregate_bwd"], "calls_per_step": kern_calls["bmkg_gat_aggregate_bwd"]}
 
-    # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) ----------------
-    cpu = None
+    # ---------------- N=1 extras: other configurations, aggregation roofline, CPU baseline ----------------
+    also, cpu = {}, None
+    if world == 1 and not args.no_also:
+        res.x = res.edge_index = None
+        graphed.clear()
+        torch.cuda.empty_cache()
+        for name in ("cfg2", "cfg1"):
+            if name != args.config:
+                try:
+                    also[name] = side_workload(name, dev, max(3, min(args.steps, 20)), 3)
+                except Exception as exc:  # noqa: BLE001
+                    also[name] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+        try:
+            if roof is not None:
+                roof["also"]["aggregation at cfg5 size (HBM)"] = aggregation_roofline(dev, peaks)
+        except Exception as exc:  # noqa: BLE001
+            roof["also"]["aggregation at cfg5 size (HBM)"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if world == 1 and not args.no_cpu_baseline:
-        rate, dt, sub = cpu_reference_step_rate(cfg, args.cpu_sample_nodes, 2, 1)
+        n_s = min(args.cpu_sample_nodes, N)
+        rate, dt, sub = cpu_reference_step_rate(cfg, n_s, 2, 1)
         cpu = {"value": rate, "unit": "nodes/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"oracle as-written GRACE step (restated PyG/PyGCL path), {sub['N']}-node / {sub['E']}-edge sample of {args.config}, fp32, 2 steps, {dt:.2f} s/step"}
 
+    config = config_dict(args.config, world, args.mode)
     line = {
         "metric": "GCL nodes/sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong" if rowshard else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['desc']}", "nodes_per_gpu": N, "edges_per_gpu": E, "modalities": M, "in_dim": IN_DIM, "cuda_graph": bool(use_graph),
-                   "hidden": HID, "conv_layers": LAYERS + 2, "tau": TAU, "parallelism": ((f"rowshard{world} (one graph; node rows split over ranks: fusion/GEMMs/aggregation/projector local, "
-                                    f"all-gather of layer inputs and of Z, InfoNCE rows split, grads all-reduced)" if full_shard else
-                                    f"rowshard{world} (one graph, replicated encoder, InfoNCE rows split over ranks, NCCL all-reduce of 1/R and dZ)")
-                                   if rowshard else f"dp{world} (per-rank graph, NCCL grad all-reduce)"),
-                   "l2_policy": "inputs larger than L2 (x is %.0f MB fp32); no explicit flush" % (x_host.numel() * 4 / 1e6),
-                   "unused_view": "computed (faithful to model/gcl.py:44)"},
+        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak" if (world > 1 and not rowshard) else "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": config,
+        "run": {"cuda_graph": bool(use_graph), "tau": TAU,
+                "l2_policy": "inputs larger than L2 (x is %.0f MB fp32, Z is %.0f MB bf16); no explicit flush" % (x_host.numel() * 4 / 1e6, 2 * N * D * 2 / 1e6)},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "final_loss": final_loss,
+        "also": also,
     }
     _emit(line)
 
@@ -445,16 +640,17 @@ def _emit(line: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
-    ap.add_argument("--cpu-sample-nodes", type=int, default=6000)
+    ap.add_argument("--config", default="cfg4", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-sample-nodes", type=int, default=8000, help="nodes of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="dp", choices=["dp", "rowshard"], help="multi-GPU mode (N>1)")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra N=1 measurements (cfg2 / cfg1 / aggregation roofline; reference arm: cfg1 / cfg2 in full)")
+    ap.add_argument("--mode", default="rowshard", choices=["rowshard", "dp"], help="multi-GPU mode (N>1): one row-sharded graph (strong) or per-rank graphs (weak)")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the run (A/B of its overhead)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay forward+backward from a CUDA graph (auto: on unless --mode rowshard)")
+                    help="replay forward+backward from a CUDA graph (auto: on unless --mode rowshard with N>1)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the end-to-end loop (default: --steps)")
     args = ap.parse_args()
     if args.impl == "ours" and args.config != "cfg5":      # W >= 3 (timing rules); cfg5 steps take seconds, 1 warm-up step is enough there
