@@ -59,7 +59,7 @@ SIGNATURES = {
     "bmkg_colsum": (I, [P, P, I64, I, P, P, SZ, P]),
     "bmkg_center_cast": (I, [P, P, I64, I, P, P]),
     "bmkg_l2norm_colsum": (I, [P, I64, I, P, P, P, SZ, P]),
-    "bmkg_center_scale": (I, [P, P, P, I64, I, F, P, P, P]),
+    "bmkg_center_scale": (I, [P, P, P, I64, I, F, P, P, P, P]),
     "bmkg_l2norm_scale_bwd": (I, [P, P, P, I64, I, F, P, P]),
     "bmkg_colmean_sigmoid": (I, [P, I64, I, P, P, SZ, P]),
     "bmkg_rowdot": (I, [P, P, I64, I, P, P]),
@@ -82,10 +82,10 @@ SIGNATURES = {
     "bmkg_infonce_stacked_rows": (I64, [I64, I64]),
     "bmkg_infonce_padded_rows": (I64, [I64, I64]),
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
-    "bmkg_infonce_fwd": (I, [P, P, I64, I, P, P, P, SZ, P]),
+    "bmkg_infonce_fwd": (I, [P, P, P, I64, I, P, P, P, SZ, P]),
     "bmkg_infonce_bwd": (I, [P, P, P, P, I64, I, P, P]),
     "bmkg_infonce_workspace_bytes_rows": (SZ, [I64, I64, I, I64, I64]),
-    "bmkg_infonce_fwd_rows": (I, [P, P, I64, I64, I, I64, I64, P, P, P, SZ, P]),
+    "bmkg_infonce_fwd_rows": (I, [P, P, P, I64, I64, I, I64, I64, P, P, P, SZ, P]),
     "bmkg_infonce_bwd_rows": (I, [P, P, P, P, I64, I64, I, I64, I64, P, P]),
 }
 

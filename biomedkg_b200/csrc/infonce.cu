@@ -89,7 +89,7 @@ __device__ __forceinline__ void stage_rows_to_tmem(const __nv_bfloat16* __restri
 template <int NP>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
-                   const __nv_bfloat16* __restrict__ z, const float* __restrict__ a /*[rows_padded], 0 beyond rows*/,
+                   const __nv_bfloat16* __restrict__ z, const float* __restrict__ w /*[rows_padded] 2^a_v, 1 for padding*/,
                    float* __restrict__ partial) {
   constexpr int D = NP * kPanelElems;
   extern __shared__ uint8_t smem_raw[];
@@ -198,7 +198,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_full);
       }
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
       for (int ct = t0; ct < t1; ++ct, ++tcount) {
         if ((tcount & 1) != wg) continue;
         const int acc = tcount % kFwdAcc;
@@ -209,7 +209,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         const bool diag = (ct == rb);
         // 128 columns in 4 chunks of 32, loads issued two chunks ahead of the exp/sum so TMEM latency is hidden
         uint32_t ra[32], rb_[32];
-        const float4* avp = reinterpret_cast<const float4*>(a + (size_t)ct * kBN);   // a_v of this tile's columns (lane-uniform)
+        const float4* wvp = reinterpret_cast<const float4*>(w + (size_t)ct * kBN);   // w_v = 2^a_v of this tile's columns (lane-uniform)
         auto consume = [&](uint32_t (&r)[32], int c) {
           if (diag) {
 #pragma unroll
@@ -218,11 +218,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 av = __ldg(avp + c * 8 + (j >> 2));
-            s0 += ex2(__uint_as_float(r[j]) + av.x);
-            s1 += ex2(__uint_as_float(r[j + 1]) + av.y);
-            s2 += ex2(__uint_as_float(r[j + 2]) + av.z);
-            s3 += ex2(__uint_as_float(r[j + 3]) + av.w);
+            // 2^(S + a_v) = 2^S w_v: the column factor rides on the accumulate (one packed FFMA per two elements) and the
+            // load is off the ex2 dependency chain
+            const float4 wv = __ldg(wvp + c * 8 + (j >> 2));
+            s01 = __ffma2_rn(make_float2(ex2(__uint_as_float(r[j])), ex2(__uint_as_float(r[j + 1]))), make_float2(wv.x, wv.y), s01);
+            s23 = __ffma2_rn(make_float2(ex2(__uint_as_float(r[j + 2])), ex2(__uint_as_float(r[j + 3]))), make_float2(wv.z, wv.w), s23);
           }
         };
         ptx::tmem_ld32(taddr, ra);
@@ -241,7 +241,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         consume(rb_, 3);
       }
       const int row = rb * kBM + lrow;
-      if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s0 + s1) + (s2 + s3);
+      if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s01.x + s01.y) + (s23.x + s23.y);
     }
   }
   ptx::tc_fence_before();
@@ -253,7 +253,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
                                                                     int row_begin, int row_end, int rows_pad_end, int N, int B, int D, float npad,
                                                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ a,
-                                                                    float2* __restrict__ qw, float* __restrict__ block_part) {
+                                                                    const float* __restrict__ w, float* __restrict__ qw,
+                                                                    float* __restrict__ block_part) {
   __shared__ float red[8];
   const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, row_end) are this launch's
   float term = 0.f;
@@ -263,10 +264,11 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
   if (u < row_end && (blk >> 1) * B + (u - blk * B) < N) {
     float R = 0.f;
     for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
-    R -= npad;                      // zero-filled out-of-range columns have a_v = 0 and contributed exactly 1.0 each
-    const float au = a[u];
-    qw[u] = make_float2(1.0f / R, exp2f(au));
-    term = logf(R) - 0.6931471805599453f * au;
+    R -= npad;                      // zero-filled out-of-range columns have w_v = 1 and contributed exactly 1.0 each
+    // qw: per PAIR of rows (q_2k, q_2k+1, w_2k, w_2k+1), so the backward's packed fp32x2 math loads register pairs directly
+    qw[(u >> 1) * 4 + (u & 1)] = 1.0f / R;
+    qw[(u >> 1) * 4 + 2 + (u & 1)] = w[u];
+    term = logf(R) - 0.6931471805599453f * a[u];
     if ((blk & 1) == 0) {   // view-1 row: positive pair with the same node's view-2 row
       const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
       const uint4* zb = reinterpret_cast<const uint4*>(z + (size_t)(u + B) * D);
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
       term -= 2.0f * 0.6931471805599453f * dot;
     }
   } else if (u < rows_pad_end) {
-    qw[u] = make_float2(0.f, 0.f);
+    qw[(u >> 1) * 4 + (u & 1)] = 0.f;
+    qw[(u >> 1) * 4 + 2 + (u & 1)] = 0.f;
   }
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
@@ -314,7 +317,7 @@ constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
-                   const float2* __restrict__ qw /*[>= ntiles*128] (q_u, w_u), zero padded*/, const float* __restrict__ mu /*[D]*/,
+                   const float* __restrict__ qw /*[>= ntiles*128][2]: (q, q, w, w) per row pair, zero padded*/, const float* __restrict__ mu /*[D]*/,
                    const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
@@ -466,15 +469,16 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
     uint32_t tcount = 0, dzphase = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float2 cu = __ldg(qw + row);  // (q_u, w_u); padded with zeros beyond `rows`
+      const float qu = __ldg(qw + (row >> 1) * 4 + (row & 1)), wu = __ldg(qw + (row >> 1) * 4 + 2 + (row & 1));   // zeros for padding rows
+      const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
       const int colbase = wg * 64;
-      float psum0 = 0.f, psum1 = 0.f;     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
+      float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
         // every tile is split between the two warpgroups (64 columns each)
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        const float4* cvp = reinterpret_cast<const float4*>(qw + gcol0);   // (q_v, w_v) pairs: one float4 = two columns
+        const float4* cvp = reinterpret_cast<const float4*>(qw + 2 * gcol0);   // (q_v, q_v+1, w_v, w_v+1): one float4 = two columns
         float4 cvr[16];  // first 32 columns: fetched before the wait so the load latency is off the S -> P chain
 #pragma unroll
         for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
@@ -490,21 +494,21 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 c01 = cvr[2 * q], c23 = cvr[2 * q + 1];
-            float p0 = ex2(__uint_as_float(r[4 * q + 0])) * fmaf(cu.x, c01.y, c01.x * cu.y);
-            float p1 = ex2(__uint_as_float(r[4 * q + 1])) * fmaf(cu.x, c01.w, c01.z * cu.y);
-            float p2 = ex2(__uint_as_float(r[4 * q + 2])) * fmaf(cu.x, c23.y, c23.x * cu.y);
-            float p3 = ex2(__uint_as_float(r[4 * q + 3])) * fmaf(cu.x, c23.w, c23.z * cu.y);
+            // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
+            const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
+            const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
+            float2 p01 = __fmul2_rn(make_float2(ex2(__uint_as_float(r[4 * q + 0])), ex2(__uint_as_float(r[4 * q + 1]))), t01);
+            float2 p23 = __fmul2_rn(make_float2(ex2(__uint_as_float(r[4 * q + 2])), ex2(__uint_as_float(r[4 * q + 3]))), t23);
             if (diag) {
               const int j = gcol0 + c * 32 + 4 * q;
-              if (j + 0 == row) p0 = 0.f;
-              if (j + 1 == row) p1 = 0.f;
-              if (j + 2 == row) p2 = 0.f;
-              if (j + 3 == row) p3 = 0.f;
+              if (j + 0 == row) p01.x = 0.f;
+              if (j + 1 == row) p01.y = 0.f;
+              if (j + 2 == row) p23.x = 0.f;
+              if (j + 3 == row) p23.y = 0.f;
             }
-            psum0 += p0 + p1;
-            psum1 += p2 + p3;
-            pk[2 * q] = pack2(p0, p1);
-            pk[2 * q + 1] = pack2(p2, p3);
+            psum = __fadd2_rn(psum, __fadd2_rn(p01, p23));
+            pk[2 * q] = pack2(p01.x, p01.y);
+            pk[2 * q + 1] = pack2(p23.x, p23.y);
           }
         };
         uint32_t pk[16];
@@ -526,7 +530,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D).  Both need the row sum of P over ALL
       // columns: exchange the two warpgroups' halves through shared memory (the next row block cannot overwrite s_rowsum
       // before every softmax warp has arrived on dz_empty, i.e. after its read below).
-      s_rowsum[wg * kBM + lrow] = psum0 + psum1;
+      s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;
       ptx::mbar_wait(dz_full, dzphase);
@@ -674,11 +678,11 @@ size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int64_t B, int D, int64_t ro
 
 size_t bmkg_infonce_workspace_bytes(int64_t N, int D) { return bmkg_infonce_workspace_bytes_rows(N, N, D, 0, 2 * N); }
 
-int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end,
-                          float* loss, float* qw, void* ws, size_t ws_bytes, void* stream) {
-  BMKG_REQUIRE(z_bf16 && a && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
+int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, int64_t N, int64_t B, int D, int64_t row_begin,
+                          int64_t row_end, float* loss, float* qw, void* ws, size_t ws_bytes, void* stream) {
+  BMKG_REQUIRE(z_bf16 && a && w && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(qw), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(w) && aligned16(qw), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
@@ -700,7 +704,7 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, int64_t N, int64_t
 #define BMKG_LAUNCH_FWD(NP_)                                                                            \
   {                                                                                                     \
     if (!set_smem(infonce_fwd_kernel<NP_>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                      \
-    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, a, partial); \
+    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_FWD(1) break;
@@ -715,15 +719,15 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, int64_t N, int64_t
   const int64_t pad_end = (row_end == rows) ? rp : row_end;
   const int nbr = (int)ceil_div(pad_end - row_begin, 256);
   infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, nslots, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
-                                                    (int)B, D, npad, zp, a, reinterpret_cast<float2*>(qw), block_part);
+                                                    (int)B, D, npad, zp, a, w, qw, block_part);
   infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nbr, 1.0f / (2.0f * (float)N), loss);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, int64_t N, int D, float* loss, float* qw, void* ws, size_t ws_bytes,
-                     void* stream) {
-  return bmkg_infonce_fwd_rows(z_bf16, a, N, N, D, 0, 2 * N, loss, qw, ws, ws_bytes, stream);
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t N, int D, float* loss, float* qw, void* ws,
+                     size_t ws_bytes, void* stream) {
+  return bmkg_infonce_fwd_rows(z_bf16, a, w, N, N, D, 0, 2 * N, loss, qw, ws, ws_bytes, stream);
 }
 
 int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t N, int64_t B, int D,
@@ -741,7 +745,7 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
   if (rc != BMKG_OK) return rc;
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
-  const float2* qwp = reinterpret_cast<const float2*>(qw);
+  const float* qwp = qw;
 #define BMKG_LAUNCH_BWD(NP_)                                                                                        \
   {                                                                                                                 \
     if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \

@@ -64,9 +64,10 @@ class CudaImpl:
         D = hs[0].size(1)
         z = torch.zeros(2, B, D, dtype=torch.bfloat16, device=mu.device)
         a = torch.zeros(2, B, dtype=torch.float32, device=mu.device)
+        w = torch.empty(2, B, dtype=torch.float32, device=mu.device)      # scratch: the gathered w is recomputed as 2^a
         for v, (h, inv) in enumerate(zip(hs, invs)):
             if h.size(0) > 0:
-                call("bmkg_center_scale", _p(h), _p(inv), _p(mu), h.size(0), D, scale, _p(z[v]), _p(a[v]), _stream())
+                call("bmkg_center_scale", _p(h), _p(inv), _p(mu), h.size(0), D, scale, _p(z[v]), _p(a[v]), _p(w[v]), _stream())
         return z, a
 
     def fwd_rows(self, Z, A, N, B, r0, r1):
@@ -74,18 +75,24 @@ class CudaImpl:
         from .ops import _p, _stream, _ws, call, lib
 
         D = Z.size(1)
+        rp = int(lib.bmkg_infonce_padded_rows(N, B))      # the kernels read a / write qw in whole 128-row tiles
+        if A.numel() < rp:
+            raise ValueError(f"a must hold bmkg_infonce_padded_rows = {rp} entries (zero beyond the stacked rows), got {A.numel()}")
         loss = torch.zeros((), dtype=torch.float32, device=Z.device)
-        qw = torch.zeros(Z.size(0), 2, dtype=torch.float32, device=Z.device)
+        qw = torch.zeros(max(Z.size(0), rp), 2, dtype=torch.float32, device=Z.device)
         if r1 > r0:
+            W = torch.exp2(A)                                # padding entries: a = 0 -> w = 1
             ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
-            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), N, B, D, r0, r1, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
+            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(W), N, B, D, r0, r1, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
         return loss, qw
 
     def bwd_rows(self, Z, QW, mu, g, N, B, r0, r1):
         """-> dZ fp32 [r1 - r0, D] of this range (the kernel addresses dz by global row: pass the buffer shifted by -r0 rows)"""
-        from .ops import _p, _stream, call
+        from .ops import _p, _stream, call, lib
 
         D = Z.size(1)
+        if QW.size(0) < int(lib.bmkg_infonce_padded_rows(N, B)):
+            raise ValueError("qw must hold bmkg_infonce_padded_rows rows (zeros for padding rows)")
         dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
         if r1 > r0:
             call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), N, B, D, r0, r1, dz.data_ptr() - r0 * D * 4, _stream())

@@ -688,6 +688,7 @@ class _InfoNCEFn(torch.autograd.Function):
         rp = int(lib.bmkg_infonce_padded_rows(N, N))
         z = torch.empty(2 * N, D, dtype=BF16, device=dev)
         a = torch.zeros(rp, dtype=torch.float32, device=dev)
+        w = torch.ones(rp, dtype=torch.float32, device=dev)
         inv_norm = torch.empty(2 * N, dtype=torch.float32, device=dev)
         cs = torch.empty(2, D, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_colsum_workspace_bytes(N, D), dev)
@@ -695,13 +696,13 @@ class _InfoNCEFn(torch.autograd.Function):
         call("bmkg_l2norm_colsum", _p(h2), N, D, inv_norm.data_ptr() + N * 4, _p(cs[1]), _p(ws), ws.numel(), _stream())
         # common vector of the centred representation z_u = mu + d_u: the column mean of the normalised, scaled rows
         mu = cs.sum(0) * (scale / (2.0 * N)) if CENTER_INFONCE else torch.zeros(D, dtype=torch.float32, device=dev)
-        call("bmkg_center_scale", _p(h1), _p(inv_norm), _p(mu), N, D, scale, _p(z), _p(a), _stream())
+        call("bmkg_center_scale", _p(h1), _p(inv_norm), _p(mu), N, D, scale, _p(z), _p(a), _p(w), _stream())
         call("bmkg_center_scale", _p(h2), inv_norm.data_ptr() + N * 4, _p(mu), N, D, scale, z.data_ptr() + N * D * 2,
-             a.data_ptr() + N * 4, _stream())
+             a.data_ptr() + N * 4, w.data_ptr() + N * 4, _stream())
         loss = torch.empty((), dtype=torch.float32, device=dev)
         qw = torch.empty(rp, 2, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
-        call("bmkg_infonce_fwd", _p(z), _p(a), N, D, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
+        call("bmkg_infonce_fwd", _p(z), _p(a), _p(w), N, D, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
         ctx.save_for_backward(h1, h2, z, inv_norm, qw, mu)
         ctx.scale = scale
         return loss

@@ -165,7 +165,7 @@ def fusion_forward(module, x, points):
     w = torch.cat([mt.q_proj.weight, mt.k_proj.weight, mt.v_proj.weight], 0)
     b = torch.cat([mt.q_proj.bias, mt.k_proj.bias, mt.v_proj.bias], 0)
     x16 = rnd(x.reshape(N * M, E), fwd="qkv" in points)
-    w16 = rnd(w, fwd="w" in points)
+    w16 = rnd(w, fwd="w" in points or "qkv" in points)        # ops._LinearFn casts both GEMM operands to bf16
     qkv = rnd(x16 @ w16.t(), fwd="qkv" in points)
     qkv = rnd(qkv + b, bwd="qkv" in points).view(N, M, 3, E)        # bias added in fp32 inside the kernel; dqkv is bf16
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
