@@ -348,7 +348,10 @@ def run_ours(args, rank, world, local_rank):
     params = [p for p in mod.model.parameters()]
     opt = torch.optim.Adam(params, lr=1e-3)
 
-    use_graph = args.graph == "on" or (args.graph == "auto" and not rowshard)
+    # CUDA-graph replay pays off when the step is launch-bound (cfg1 / cfg2: a few ms of 5-50 us kernels).  At cfg4 / cfg5 the step
+    # is ~100 ms of long kernels, and a captured graph would pin the InfoNCE E store (up to 135 GB) in a private memory pool per
+    # capture - so those run eagerly, where torch's caching allocator hands the same block back every step.
+    use_graph = args.graph == "on" or (args.graph == "auto" and not rowshard and N <= 50_000)
     graphed = {}      # "resident" / "e2e" -> GraphedStep (captured lazily, after the eager warm-up)
 
     def tail():
@@ -487,6 +490,7 @@ def run_ours(args, rank, world, local_rank):
 
     e2e_graph = use_graph
     if e2e_graph:
+        graphed.pop("resident", None)          # release its memory pool before the second capture
         opt.zero_grad(set_to_none=True)
         try:
             graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True)    # every step brings its own edge_index: sort captured too

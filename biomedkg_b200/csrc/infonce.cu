@@ -53,6 +53,7 @@ constexpr int kTmemCols = 512;
 // it from shared memory for every MMA and the kernel is smem-bandwidth bound.
 constexpr int kFwdStages = 3, kFwdAcc = 3, kFwdPanelBytes = kBN * 128;
 constexpr size_t kFwdSmemBytes = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages + 256;
+constexpr int kETileBytes = kBM * kBN * 2;   // one stored tile of E = 2^S (bf16): 32 KB
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -90,7 +91,7 @@ template <int NP>  // NP = D / 64 (number of 64-column K panels), compile-time s
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ w /*[rows_padded] 2^a_v, 1 for padding*/,
-                   float* __restrict__ partial) {
+                   float* __restrict__ partial, uint8_t* __restrict__ e_store /*nullable: bf16 2^S tiles for the backward*/) {
   constexpr int D = NP * kPanelElems;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -210,6 +211,9 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         // 128 columns in 4 chunks of 32, loads issued two chunks ahead of the exp/sum so TMEM latency is hidden
         uint32_t ra[32], rb_[32];
         const float4* wvp = reinterpret_cast<const float4*>(w + (size_t)ct * kBN);   // w_v = 2^a_v of this tile's columns (lane-uniform)
+        // stored-E mode: this thread's row of the tile, 16 B (8 columns) at a time, chunk-major inside the 32 KB tile
+        // (offset = chunk * 2048 + row * 16) so that a warp writes 512 contiguous bytes and the backward reads it conflict-free
+        uint8_t* etile = e_store ? e_store + ((size_t)(rb - sch.rb0) * sch.ntiles + ct) * kETileBytes + (size_t)lrow * 16 : nullptr;
         auto consume = [&](uint32_t (&r)[32], int c) {
           if (diag) {
 #pragma unroll
@@ -217,12 +221,21 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
               if (c * 32 + j == lrow) r[j] = 0xff800000u;  // -inf -> ex2 = 0
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 32; j += 8) {
             // 2^(S + a_v) = 2^S w_v: the column factor rides on the accumulate (one packed FFMA per two elements) and the
             // load is off the ex2 dependency chain
-            const float4 wv = __ldg(wvp + c * 8 + (j >> 2));
-            s01 = __ffma2_rn(make_float2(ex2(__uint_as_float(r[j])), ex2(__uint_as_float(r[j + 1]))), make_float2(wv.x, wv.y), s01);
-            s23 = __ffma2_rn(make_float2(ex2(__uint_as_float(r[j + 2])), ex2(__uint_as_float(r[j + 3]))), make_float2(wv.z, wv.w), s23);
+            const float4 wa = __ldg(wvp + c * 8 + (j >> 2)), wb = __ldg(wvp + c * 8 + (j >> 2) + 1);
+            const float2 e01 = make_float2(ex2(__uint_as_float(r[j])), ex2(__uint_as_float(r[j + 1])));
+            const float2 e23 = make_float2(ex2(__uint_as_float(r[j + 2])), ex2(__uint_as_float(r[j + 3])));
+            const float2 e45 = make_float2(ex2(__uint_as_float(r[j + 4])), ex2(__uint_as_float(r[j + 5])));
+            const float2 e67 = make_float2(ex2(__uint_as_float(r[j + 6])), ex2(__uint_as_float(r[j + 7])));
+            s01 = __ffma2_rn(e01, make_float2(wa.x, wa.y), s01);
+            s23 = __ffma2_rn(e23, make_float2(wa.z, wa.w), s23);
+            s01 = __ffma2_rn(e45, make_float2(wb.x, wb.y), s01);
+            s23 = __ffma2_rn(e67, make_float2(wb.z, wb.w), s23);
+            if (etile)
+              __stcs(reinterpret_cast<uint4*>(etile + (size_t)(c * 4 + (j >> 3)) * 2048),
+                     make_uint4(pack2(e01.x, e01.y), pack2(e23.x, e23.y), pack2(e45.x, e45.y), pack2(e67.x, e67.y)));
           }
         };
         ptx::tmem_ld32(taddr, ra);
@@ -578,6 +591,228 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 }
 
 // ----------------------------------------------------------------------------
+// backward from stored E  (no recomputation: 16 N^2 D -> 8 N^2 D executed)
+// ----------------------------------------------------------------------------
+// When the forward was asked to keep E = 2^S (bf16, 8 N^2 bytes per launch range - the forward is tensor/MUFU-bound, its HBM
+// write port is idle), the backward streams the E tiles back with 1-D bulk copies instead of recomputing S on the tensor pipe
+// and re-exponentiating: the softmax warpgroups read their row of the tile from shared memory (chunk-major layout: one
+// conflict-free LDS.128 per 8 columns), scale it to P = E (q_u w_v + q_v w_u) with packed fp32x2 math, write bf16 P to TMEM and
+// MMA2 (dZ += P Z_V, A from TMEM, B = the Z_V tile read MN-major) is the only tensor work left.  E_uu was stored as 0, so
+// there is no diagonal handling.  HBM-bound on the E read (32 KB per 8.4 MFLOP tile = 5.3 TB/s at the sustained bf16 rate).
+// TMEM map: [0,256) dZ accumulator, [256,384) / [384,512) P buffers (64 of the 128 columns used, as in the kernel above).
+// smem: 2 stages x (Z_V tile 64 KB + E tile 32 KB).
+constexpr size_t kBwdESmemBytes = 1024 + 2 * ((size_t)kFwdPanelBytes * kMaxPanels + kETileBytes) + 256 + 2 * kBM * sizeof(float);
+
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
+                     const float* __restrict__ qw, const float* __restrict__ mu, const float* __restrict__ gscale,
+                     const __nv_bfloat16* __restrict__ z, const uint8_t* __restrict__ e_store, float* __restrict__ dz) {
+  constexpr int D = NP * kPanelElems;
+  constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
+  constexpr int kZStage = kPB * kMaxPanels;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  uint8_t* sB = smem;                          // [2][64 KB] Z_V tiles
+  uint8_t* sE = smem + 2 * kZStage;            // [2][32 KB] E tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 2 * kETileBytes);
+  uint64_t* full = bars;                    // [2] Z_V tile + E tile landed (transaction bytes)
+  uint64_t* empty = full + 2;               // [2] Z_V stage free (MMA2 of its tile retired)
+  uint64_t* e_empty = empty + 2;            // [2] E stage free (8 softmax warps have read it)
+  uint64_t* p_full = e_empty + 2;           // [2][4] P written per 32-column quarter (4 warp arrivals each)
+  uint64_t* p_empty = p_full + 8;           // [2] P buffer free (MMA2 of its tile retired)
+  uint64_t* dz_full = p_empty + 2;
+  uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
+  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 warpgroups][128 rows]
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&e_empty[s], 8);
+      ptx::mbar_init(&p_empty[s], 1);
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
+    }
+    ptx::mbar_init(dz_full, 1);
+    ptx::mbar_init(dz_empty, 8);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmap);
+  }
+  if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tile_bytes = (uint32_t)NP * kPB;
+  constexpr uint32_t kColS = 256u;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer: Z_V tile (MMA2's B operand) + E tile ----------------
+      uint32_t tcount = 0;
+      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+        const uint8_t* erow = e_store + (size_t)(rb - rb0) * ntiles * kETileBytes;
+        for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+          const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+          ptx::mbar_wait(&empty[b], ph ^ 1);
+          ptx::mbar_wait(&e_empty[b], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[b], tile_bytes + (uint32_t)kETileBytes);
+          uint8_t* dst = sB + (size_t)b * kZStage;
+          for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[b], p * kPanelElems, ct * kBN);
+          ptx::bulk_load_1d(sE + (size_t)b * kETileBytes, erow + (size_t)ct * kETileBytes, (uint32_t)kETileBytes, &full[b]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: dZ += P(tmem) Z_V(smem, MN-major) ----------------
+    constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);
+    uint64_t bdesc_mn[2];
+    for (int st = 0; st < 2; ++st) bdesc_mn[st] = ptx::smem_desc_sw128(ptx::smem_u32(sB + (size_t)st * kZStage), kPB, 1024);
+    uint32_t tcount = 0, dzphase = 0;
+    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+      ptx::mbar_wait(dz_empty, dzphase ^ 1);
+      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+        const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+        const uint64_t bmn = bdesc_mn[b];
+        const uint32_t p_tmem = tmem_base + kColS + b * 128u;
+        ptx::mbar_wait(&full[b], ph);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ptx::mbar_wait(&p_full[b * 4 + q], ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const int k0 = 4 * (q & 1) + 2 * (q >> 1);   // quarter q = 2*chunk + wg covers columns [64 wg + 32 chunk, +32)
+#pragma unroll
+            for (int k = k0; k < k0 + 2; ++k) {
+              ptx::umma_ts(tmem_base, p_tmem + (uint32_t)(k >> 2) * 64u + (uint32_t)(k & 3) * 8u, bmn + (uint32_t)(k * 2048 >> 4), idesc2,
+                           (ct > 0 || q > 0 || k > k0) ? 1u : 0u);
+            }
+            if (q == 3) {
+              ptx::umma_commit(&empty[b]);
+              ptx::umma_commit(&p_empty[b]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(dz_full);
+      __syncwarp();
+      dzphase ^= 1;
+    }
+  } else {  // ---------------- scaling / epilogue warpgroups ----------------
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
+    uint32_t tcount = 0, dzphase = 0;
+    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+      const int row = rb * kBM + lrow;
+      const float qu = __ldg(qw + (row >> 1) * 4 + (row & 1)), wu = __ldg(qw + (row >> 1) * 4 + 2 + (row & 1));   // zeros for padding rows
+      const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
+      const int colbase = wg * 64;
+      float2 psum = make_float2(0.f, 0.f);
+      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+        const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
+        const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
+        const int gcol0 = ct * kBN + colbase;
+        const float4* cvp = reinterpret_cast<const float4*>(qw + 2 * gcol0);   // (q_v, q_v+1, w_v, w_v+1): one float4 = two columns
+        float4 cvr[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
+        ptx::mbar_wait(&full[b], ph);
+        // this thread's row, columns [64 wg, 64 wg + 64): 16-byte chunks 8 wg .. 8 wg + 7 of the chunk-major tile
+        const uint4* ep = reinterpret_cast<const uint4*>(sE + (size_t)b * kETileBytes + (size_t)(wg * 8) * 2048 + (size_t)lrow * 16);
+        uint4 ev[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ev[i] = ep[i * 128];   // 2048 B apart
+        auto make_p = [&](int c, uint32_t (&pk)[16]) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = ev[c * 4 + i];
+            const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {   // two columns per 32-bit word
+              const float4 cv = cvr[i * 4 + h];
+              const float2 t = __ffma2_rn(qu2, make_float2(cv.z, cv.w), __fmul2_rn(make_float2(cv.x, cv.y), wu2));
+              const float2 p = __fmul2_rn(make_float2(__uint_as_float(wds[h] << 16), __uint_as_float(wds[h] & 0xffff0000u)), t);
+              psum = __fadd2_rn(psum, p);
+              pk[i * 4 + h] = pack2(p.x, p.y);
+            }
+          }
+        };
+        uint32_t pk[16];
+        ptx::mbar_wait(&p_empty[b], ph ^ 1);   // MMA2 of the tile that used this P buffer two tiles ago has retired
+        ptx::tc_fence_after();
+        make_p(0, pk);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 16 + q);
+        ptx::tmem_st16(taddr, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + wg]);
+        make_p(1, pk);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&e_empty[b]);   // every lane has consumed its E registers' source: the stage may be refilled
+        ptx::tmem_st16(taddr + 16, pk);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + 2 + wg]);
+      }
+      s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;
+      ptx::mbar_wait(dz_full, dzphase);
+      dzphase ^= 1;
+      ptx::tc_fence_after();
+      const int half = D / 2;
+      const int blk = row / B;
+      const int pair = (blk & 1) ? row - B : row + B;
+      const bool valid = (blk >> 1) * B + (row - blk * B) < N;
+      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          const uint4* zp = reinterpret_cast<const uint4*>(z + (size_t)pair * D + c0);
+          float* out = dz + (size_t)row * D + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+            unpack8(__ldg(zp + q), f);
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mu + c0 + 8 * q));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mu + c0 + 8 * q + 4));
+            float4 o0, o1;
+            o0.x = gcoef * (fmaf(m0.x, prow, __uint_as_float(r[8 * q + 0])) - 2.f * f[0]);
+            o0.y = gcoef * (fmaf(m0.y, prow, __uint_as_float(r[8 * q + 1])) - 2.f * f[1]);
+            o0.z = gcoef * (fmaf(m0.z, prow, __uint_as_float(r[8 * q + 2])) - 2.f * f[2]);
+            o0.w = gcoef * (fmaf(m0.w, prow, __uint_as_float(r[8 * q + 3])) - 2.f * f[3]);
+            o1.x = gcoef * (fmaf(m1.x, prow, __uint_as_float(r[8 * q + 4])) - 2.f * f[4]);
+            o1.y = gcoef * (fmaf(m1.y, prow, __uint_as_float(r[8 * q + 5])) - 2.f * f[5]);
+            o1.z = gcoef * (fmaf(m1.z, prow, __uint_as_float(r[8 * q + 6])) - 2.f * f[6]);
+            o1.w = gcoef * (fmaf(m1.w, prow, __uint_as_float(r[8 * q + 7])) - 2.f * f[7]);
+            *reinterpret_cast<float4*>(out + 8 * q) = o0;
+            *reinterpret_cast<float4*>(out + 8 * q + 4) = o1;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dz_empty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -678,11 +913,19 @@ size_t bmkg_infonce_workspace_bytes_rows(int64_t N, int64_t B, int D, int64_t ro
 
 size_t bmkg_infonce_workspace_bytes(int64_t N, int D) { return bmkg_infonce_workspace_bytes_rows(N, N, D, 0, 2 * N); }
 
+// bytes of the optional E = 2^S store of a row range: one 32 KB bf16 tile per (128-row block of the range, 128-column tile)
+size_t bmkg_infonce_e_store_bytes(int64_t N, int64_t B, int64_t row_begin, int64_t row_end) {
+  if (!block_ok(N, B)) return 0;
+  const int64_t rows = stacked_rows(N, B);
+  if (!rows_range_ok(rows, row_begin, row_end)) return 0;
+  return (size_t)ceil_div(row_end - row_begin, kBM) * (size_t)ceil_div(rows, kBN) * kETileBytes;
+}
+
 int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, int64_t N, int64_t B, int D, int64_t row_begin,
-                          int64_t row_end, float* loss, float* qw, void* ws, size_t ws_bytes, void* stream) {
+                          int64_t row_end, float* loss, float* qw, void* e_store, void* ws, size_t ws_bytes, void* stream) {
   BMKG_REQUIRE(z_bf16 && a && w && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(w) && aligned16(qw), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(w) && aligned16(qw) && aligned16(e_store), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
@@ -704,7 +947,7 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
 #define BMKG_LAUNCH_FWD(NP_)                                                                            \
   {                                                                                                     \
     if (!set_smem(infonce_fwd_kernel<NP_>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                      \
-    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial); \
+    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, static_cast<uint8_t*>(e_store)); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_FWD(1) break;
@@ -725,16 +968,16 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
   return BMKG_OK;
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t N, int D, float* loss, float* qw, void* ws,
-                     size_t ws_bytes, void* stream) {
-  return bmkg_infonce_fwd_rows(z_bf16, a, w, N, N, D, 0, 2 * N, loss, qw, ws, ws_bytes, stream);
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t N, int D, float* loss, float* qw, void* e_store,
+                     void* ws, size_t ws_bytes, void* stream) {
+  return bmkg_infonce_fwd_rows(z_bf16, a, w, N, N, D, 0, 2 * N, loss, qw, e_store, ws, ws_bytes, stream);
 }
 
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t N, int64_t B, int D,
-                          int64_t row_begin, int64_t row_end, float* dz, void* stream) {
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store, int64_t N,
+                          int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
   BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu) && aligned16(e_store), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
@@ -746,6 +989,23 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
   const float* qwp = qw;
+  if (e_store) {   // the forward kept E = 2^S for this row range: stream it back instead of recomputing S
+    const uint8_t* ep = static_cast<const uint8_t*>(e_store);
+#define BMKG_LAUNCH_BWDE(NP_)                                                                                      \
+  {                                                                                                                 \
+    if (!set_smem(infonce_bwd_e_kernel<NP_>, kBwdESmemBytes)) return BMKG_ERR_LAUNCH;                               \
+    infonce_bwd_e_kernel<NP_><<<grid, kThreads, kBwdESmemBytes, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, ep, dz); \
+  }
+    switch (D / kPanelElems) {
+      case 1: BMKG_LAUNCH_BWDE(1) break;
+      case 2: BMKG_LAUNCH_BWDE(2) break;
+      case 3: BMKG_LAUNCH_BWDE(3) break;
+      default: BMKG_LAUNCH_BWDE(4) break;
+    }
+#undef BMKG_LAUNCH_BWDE
+    BMKG_CHECK_LAUNCH();
+    return BMKG_OK;
+  }
 #define BMKG_LAUNCH_BWD(NP_)                                                                                        \
   {                                                                                                                 \
     if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \
@@ -762,9 +1022,9 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
   return BMKG_OK;
 }
 
-int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t N, int D, float* dz,
-                     void* stream) {
-  return bmkg_infonce_bwd_rows(z_bf16, qw, mu, gscale, N, N, D, 0, 2 * N, dz, stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store, int64_t N, int D,
+                     float* dz, void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, qw, mu, gscale, e_store, N, N, D, 0, 2 * N, dz, stream);
 }
 
 }  // extern "C"

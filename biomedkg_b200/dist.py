@@ -80,10 +80,15 @@ class CudaImpl:
             raise ValueError(f"a must hold bmkg_infonce_padded_rows = {rp} entries (zero beyond the stacked rows), got {A.numel()}")
         loss = torch.zeros((), dtype=torch.float32, device=Z.device)
         qw = torch.zeros(max(Z.size(0), rp), 2, dtype=torch.float32, device=Z.device)
+        self.e_store = None
         if r1 > r0:
+            from .ops import alloc_e_store
+
             W = torch.exp2(A)                                # padding entries: a = 0 -> w = 1
             ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
-            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(W), N, B, D, r0, r1, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
+            self.e_store = alloc_e_store(N, B, r0, r1, Z.device)      # E = 2^S of this rank's rows, kept for the backward if it fits
+            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(W), N, B, D, r0, r1, _p(loss), _p(qw), _p(self.e_store), _p(ws), ws.numel(),
+                 _stream())
         return loss, qw
 
     def bwd_rows(self, Z, QW, mu, g, N, B, r0, r1):
@@ -95,7 +100,9 @@ class CudaImpl:
             raise ValueError("qw must hold bmkg_infonce_padded_rows rows (zeros for padding rows)")
         dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
         if r1 > r0:
-            call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), N, B, D, r0, r1, dz.data_ptr() - r0 * D * 4, _stream())
+            call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), _p(getattr(self, "e_store", None)), N, B, D, r0, r1,
+                 dz.data_ptr() - r0 * D * 4, _stream())
+            self.e_store = None
         return dz
 
     def norm_bwd(self, h, inv, dz, scale):

@@ -702,23 +702,47 @@ class _InfoNCEFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         qw = torch.empty(rp, 2, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
-        call("bmkg_infonce_fwd", _p(z), _p(a), _p(w), N, D, _p(loss), _p(qw), _p(ws), ws.numel(), _stream())
-        ctx.save_for_backward(h1, h2, z, inv_norm, qw, mu)
+        e_store = alloc_e_store(N, N, 0, 2 * N, dev) if any(ctx.needs_input_grad[:2]) else None      # only a backward reads it
+        call("bmkg_infonce_fwd", _p(z), _p(a), _p(w), N, D, _p(loss), _p(qw), _p(e_store), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(h1, h2, z, inv_norm, qw, mu, e_store)
         ctx.scale = scale
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        h1, h2, z, inv_norm, qw, mu = ctx.saved_tensors
+        h1, h2, z, inv_norm, qw, mu, e_store = ctx.saved_tensors
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        call("bmkg_infonce_bwd", _p(z), _p(qw), _p(mu), _p(g), N, D, _p(dz), _stream())
+        call("bmkg_infonce_bwd", _p(z), _p(qw), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _stream())
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())
         call("bmkg_l2norm_scale_bwd", _p(h2), inv_norm.data_ptr() + N * 4, dz.data_ptr() + N * D * 4, N, D, ctx.scale, _p(dh2),
              _stream())
         return dh1, dh2, None
+
+
+#: Stored-E backward (csrc/infonce.cu): the forward keeps E = 2^S as bf16 (8 N^2 bytes for a full launch) so the backward does
+#: not recompute the similarities.  Used when the buffer fits in this fraction of the currently free device memory (and under
+#: the absolute cap, bytes); 0 disables it (the recomputing backward).  A fixed-shape training loop allocates the buffer from
+#: torch's caching allocator every step, i.e. without a device allocation after the first.
+E_STORE_FREE_FRACTION = float(_os.environ.get("BMKG_E_STORE_FRACTION", "0.8"))
+E_STORE_MAX_BYTES = int(float(_os.environ.get("BMKG_E_STORE_MAX_GB", "150")) * 2**30)
+_E_STORE_DECISION: dict = {}
+
+
+def alloc_e_store(N, B, r0, r1, device):
+    """uint8 buffer for the E store of rows [r0, r1), or None when it does not fit (decided once per shape and device)."""
+    need = int(lib.bmkg_infonce_e_store_bytes(N, B, r0, r1))
+    if need == 0 or E_STORE_FREE_FRACTION <= 0:
+        return None
+    key = (need, torch.device(device).index)
+    ok = _E_STORE_DECISION.get(key)
+    if ok is None:
+        free, _ = torch.cuda.mem_get_info(device)
+        cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)      # reusable without a new device allocation
+        ok = _E_STORE_DECISION[key] = need <= min(E_STORE_MAX_BYTES, E_STORE_FREE_FRACTION * (free + cached))
+    return torch.empty(need, dtype=torch.uint8, device=device) if ok else None
 
 
 #: centre the InfoNCE operand on its column mean (False = plain bf16 rows, mu = 0; only for A/B numerics tests)

@@ -228,14 +228,18 @@ int bmkg_redaf_bwd(const void* t_bf16, const float* bias, const float* gate, con
  *   contiguous, 128-aligned range - the unit of the row-sharded multi-GPU path.
  * fwd writes the scalar loss and qw fp32 [P][2], an opaque hand-over to bwd: per pair of rows (q_2k, q_2k+1, w_2k, w_2k+1) with
  * q_u = 1/R'_u, R'_u = sum_{v != u} 2^(d_u.d_v + a_v) (zeros for padding rows); bwd writes dL/dz fp32 [R, D] (valid rows only) scaled by *gscale:
- *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],  P_uv = 2^(d_u.d_v) (q_u w_v + q_v w_u). */
+ *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],  P_uv = 2^(d_u.d_v) (q_u w_v + q_v w_u).
+ * Optional E store: pass e_store (bmkg_infonce_e_store_bytes bytes, 16-byte aligned; NULL = off) to fwd and the SAME buffer to
+ * bwd: the forward then also writes E = 2^(d_u.d_v) as bf16 tiles and the backward streams them back instead of recomputing
+ * the similarities (16 N^2 D -> 8 N^2 D executed; 8 N^2 bytes of HBM per full-range launch - the caller decides whether it fits). */
 int64_t bmkg_infonce_stacked_rows(int64_t num_nodes, int64_t view_block);
+size_t bmkg_infonce_e_store_bytes(int64_t num_nodes, int64_t view_block, int64_t row_begin, int64_t row_end);
 int64_t bmkg_infonce_padded_rows(int64_t num_nodes, int64_t view_block);
 size_t bmkg_infonce_workspace_bytes(int64_t num_nodes, int dim);
 int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t num_nodes, int dim, float* loss, float* qw,
-                     void* ws, size_t ws_bytes, void* stream);
-int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t num_nodes, int dim,
-                     float* dz, void* stream);
+                     void* e_store, void* ws, size_t ws_bytes, void* stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store,
+                     int64_t num_nodes, int dim, float* dz, void* stream);
 /* Row-range variants: only rows [row_begin, row_end) of the stacked matrix are processed against ALL columns.
  * row_begin % 128 == 0; row_end % 128 == 0 or row_end == R.  fwd_rows writes this range's share of the loss (the shares of
  * all ranges add up to the loss) and qw for the range; bwd_rows needs qw for all rows (all-gathered) and writes dz rows of
@@ -243,9 +247,11 @@ int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const
  * -row_begin * D elements for a range-local buffer). */
 size_t bmkg_infonce_workspace_bytes_rows(int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end);
 int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, int64_t num_nodes, int64_t view_block, int dim,
-                          int64_t row_begin, int64_t row_end, float* loss, float* qw, void* ws, size_t ws_bytes, void* stream);
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, int64_t num_nodes,
-                          int64_t view_block, int dim, int64_t row_begin, int64_t row_end, float* dz, void* stream);
+                          int64_t row_begin, int64_t row_end, float* loss, float* qw, void* e_store, void* ws, size_t ws_bytes,
+                          void* stream);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store,
+                          int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end, float* dz,
+                          void* stream);
 
 #ifdef __cplusplus
 }

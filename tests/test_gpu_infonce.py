@@ -12,8 +12,20 @@ DEV = "cuda"
 CASES = [(5, 64), (64, 64), (128, 256), (200, 128), (1000, 256), (1025, 192), (4096, 256), (6000, 256), (300, 100), (257, 40)]
 
 
+@pytest.fixture(params=["stored_e", "recompute"])
+def backward_variant(request, monkeypatch):
+    """Both backward kernels: 'stored_e' (the forward keeps E = 2^S, the backward streams it back: infonce_bwd_e_kernel) and
+    'recompute' (infonce_bwd_kernel, what runs when the 8 N^2-byte store does not fit)."""
+    from biomedkg_b200 import ops
+
+    monkeypatch.setattr(ops, "E_STORE_FREE_FRACTION", 0.8 if request.param == "stored_e" else 0.0)
+    ops._E_STORE_DECISION.clear()
+    yield request.param
+    ops._E_STORE_DECISION.clear()
+
+
 @pytest.mark.parametrize("n,d", CASES)
-def test_infonce_forward_backward(n, d):
+def test_infonce_forward_backward(n, d, backward_variant):
     from biomedkg_b200 import ops
 
     g = torch.Generator().manual_seed(n * 7 + d)
@@ -47,7 +59,7 @@ def test_infonce_deterministic_and_scale_invariant():
     assert abs(float(ls) - float(l0)) < 1e-5 * abs(float(l0))
 
 
-def test_infonce_full_size_cfg2_properties():
+def test_infonce_full_size_cfg2_properties(backward_variant):
     """N = 28k (BASELINE cfg 2): the [N,2N] oracle needs >40 GB, so check size-independent properties:
     identical views give loss = log-sum bound behaviour, and the gradient of sum-normalised rows is
     orthogonal to h (normalisation), and the loss matches a blockwise fp32 torch evaluation on the GPU."""
@@ -112,7 +124,7 @@ def _stacked_operand(h1, h2, B, tau=0.2):
 
 @pytest.mark.parametrize("n,d,B,splits", [(1000, 256, 1000, (0, 768, 2000)), (300, 64, 128, (0, 256, 512, 768)),
                                           (4096, 256, 1024, (0, 2048, 4096, 8192)), (1000, 256, 384, (0, 768, 1536, 2304))])
-def test_row_range_entry_points_compose(n, d, B, splits):
+def test_row_range_entry_points_compose(n, d, B, splits, backward_variant):
     """bmkg_infonce_{fwd,bwd}_rows over disjoint row ranges of the block-interleaved layout (what each rank of the row-sharded
     multi-GPU path runs; B = that path's node block, with zero padding rows when B does not divide N) add up to the
     single-launch result of the plain [h1; h2] layout: loss shares sum to the loss, every node's gradient is identical."""
@@ -130,12 +142,16 @@ def test_row_range_entry_points_compose(n, d, B, splits):
     gs = torch.ones((), device=DEV)
     loss = torch.zeros((), device=DEV)
     QW = torch.zeros(A.numel(), 2, device=DEV)
-    for r0, r1 in zip(splits, splits[1:]):
-        l, qw = impl.fwd_rows(Z, A, n, B, r0, r1)
+    from biomedkg_b200.dist import CudaImpl
+
+    ranks = [CudaImpl() for _ in splits[1:]]       # one per range, as one per rank: each keeps its own E store for its backward
+    for impl_r, r0, r1 in zip(ranks, splits, splits[1:]):
+        l, qw = impl_r.fwd_rows(Z, A, n, B, r0, r1)
         loss += l
         QW[r0:r1] = qw[r0:r1]
+        assert (impl_r.e_store is not None) == (backward_variant == "stored_e")
     assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref)), (float(loss), float(ref))
-    dz = torch.cat([impl.bwd_rows(Z, QW, mu, gs, n, B, r0, r1)[: r1 - r0] for r0, r1 in zip(splits, splits[1:])])
+    dz = torch.cat([impl_r.bwd_rows(Z, QW, mu, gs, n, B, r0, r1)[: r1 - r0] for impl_r, r0, r1 in zip(ranks, splits, splits[1:])])
     dz = dz.view(-1, 2, B, d)                                                  # [block, view, row, D]
     dz1 = dz[:, 0].reshape(-1, d)[:n].contiguous()
     dz2 = dz[:, 1].reshape(-1, d)[:n].contiguous()
@@ -146,7 +162,7 @@ def test_row_range_entry_points_compose(n, d, B, splits):
 
 
 @pytest.mark.parametrize("n,d,eps", [(2000, 256, 1e-3), (777, 128, 3e-3), (6000, 256, 3e-4)])
-def test_infonce_near_collapsed_embeddings(n, d, eps):
+def test_infonce_near_collapsed_embeddings(n, d, eps, backward_variant):
     """The regime GRACE starts in (and that every synthetic BASELINE config is in): all rows share one direction and
     differ by eps.  The loss sits at ln(2N-1) and the gradient lives entirely in the deviations - a plain bf16 operand
     (2^-9) cannot resolve them; the centred operand (fp32 common vector + bf16 deviations) must: gradients <= 1e-2 of the
@@ -215,11 +231,24 @@ def test_infonce_cluster_closed_form_large_n(n):
     R = (nc - 1.0) * math.exp(1.0 / tau) + (2.0 * n - nc)                      # exact-arithmetic value: the stated tolerance
     exact = float((torch.log(R) * nc).sum() / (2.0 * n) - 1.0 / tau)
     assert abs(float(loss) - exact) <= 1e-3 * abs(exact)
-    G = nc[None, :] * (1.0 / R[:, None] + 1.0 / R[None, :]) / (2.0 * n * tau)
-    G.fill_diagonal_(0.0)
+    # gradient the device's operand implies (same K-cluster collapse): dz_c = ln2/2N [sum_c' n_c' P_cc' zt_c' - P_cc zt_c - 2 zt_c],
+    # P_cc' = 2^G_cc' (1/R_c + 1/R_c'), then the normalisation backward dh_u = s (dz_c - e_c dz_c[c]) (|h_u| = 1)
+    P = torch.exp2(G) * (1.0 / Rk[:, None] + 1.0 / Rk[None, :])
+    dzk = (math.log(2.0) / (2.0 * n)) * ((P * nc[None, :]) @ zt - torch.diagonal(P)[:, None] * zt - 2.0 * zt)
+    dzk[torch.arange(K), torch.arange(K)] = 0.0                                # minus the component along h_u = e_c
+    gdev = (float(s32) * dzk)[c]
+    # ... and the exact-arithmetic gradient (no rounding anywhere)
+    Gx = nc[None, :] * (1.0 / R[:, None] + 1.0 / R[None, :]) / (2.0 * n * tau)
+    Gx.fill_diagonal_(0.0)
     gref = torch.zeros(n, d, dtype=torch.float64)
-    gref[:, :K] = G[c]
+    gref[:, :K] = Gx[c]
     for got in (h1.grad, h2.grad):
-        assert rel_err(got, gref) < 1e-2
-        row_err = (got.double().cpu() - gref).norm(dim=1) / gref.norm(dim=1)
-        assert float(row_err.max()) < 2e-2                                     # every row, not just on average
+        # kernel exactness: against the gradient of the operand the device actually holds (bf16 P is the only rounding left,
+        # and here it is coherent - every same-cluster-pair entry is the same number)
+        assert rel_err(got, gdev) < 4e-3, rel_err(got, gdev)
+        row_err = (got.double().cpu() - gdev).norm(dim=1) / gdev.norm(dim=1)
+        assert float(row_err.max()) < 1e-2                                     # every row, not just on average
+        # against exact arithmetic this input is the format's worst case: all rows of a cluster are the SAME vector, so the
+        # bf16 rounding of its one large component (up to 2^-9 of 2.7) shifts a whole block of similarities coherently
+        # (up to 0.03 in log2 units = 2 % of 2^S) instead of averaging out as it does for generic rows
+        assert rel_err(got, gref) < 3e-2
