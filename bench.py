@@ -587,8 +587,11 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- N=1 extras: other configurations, aggregation roofline, CPU baseline ----------------
     also, cpu = {}, None
     if world == 1 and not args.no_also:
+        from biomedkg_b200 import ops as _ops
+
         res.x = res.edge_index = None
         graphed.clear()
+        _ops.drop_e_store_pool()               # the headline workload's E store (up to 126 GiB) goes back to the device
         torch.cuda.empty_cache()
         for name in ("cfg2", "cfg1"):
             if name != args.config:

@@ -54,6 +54,9 @@ constexpr int kTmemCols = 512;
 constexpr int kFwdStages = 3, kFwdAcc = 3, kFwdPanelBytes = kBN * 128;
 constexpr size_t kFwdSmemBytes = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages + 256;
 constexpr int kETileBytes = kBM * kBN * 2;   // one stored tile of E = 2^S (bf16): 32 KB
+// stored-E forward: 2 column-tile stages + one E staging tile per softmax warpgroup (written out by a TMA bulk store)
+constexpr int kFwdStagesStore = 2;
+constexpr size_t kFwdSmemBytesStore = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStagesStore + 2 * (size_t)kETileBytes + 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -87,7 +90,7 @@ __device__ __forceinline__ void stage_rows_to_tmem(const __nv_bfloat16* __restri
 // forward
 // ----------------------------------------------------------------------------
 // TMEM map: [0,128) stationary rows A (bf16), [128 + 128 i, +128) accumulator ring i = 0..2.
-template <int NP>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
+template <int NP, bool STORE>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ w /*[rows_padded] 2^a_v, 1 for padding*/,
@@ -96,11 +99,13 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  constexpr int kStages = STORE ? kFwdStagesStore : kFwdStages;
   uint8_t* sB = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages);
-  uint64_t* full = bars;                       // [kFwdStages]
-  uint64_t* empty = full + kFwdStages;         // [kFwdStages]
-  uint64_t* a_full = empty + kFwdStages;       // stationary rows staged in TMEM (4 warp arrivals)
+  uint8_t* sE = smem + (size_t)kFwdPanelBytes * kMaxPanels * kStages;   // STORE: [2 warpgroups][32 KB] E staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (STORE ? 2 * kETileBytes : 0));
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = full + kStages;            // [kStages]
+  uint64_t* a_full = empty + kStages;          // stationary rows staged in TMEM (4 warp arrivals)
   uint64_t* a_empty = a_full + 1;              // every MMA of the work item retired
   uint64_t* tfull = a_empty + 1;               // [kFwdAcc]
   uint64_t* tempty = tfull + kFwdAcc;          // [kFwdAcc]
@@ -111,7 +116,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kFwdStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(a_full, 4);
     ptx::mbar_init(a_empty, 1);
     for (int b = 0; b < kFwdAcc; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
@@ -140,7 +145,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           uint8_t* dst = sB + (size_t)stage * kFwdPanelBytes * kMaxPanels;
           for (int p = 0; p < npanels; ++p)
             ptx::tma_load_2d(dst + p * kFwdPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
-          if (++stage == kFwdStages) { stage = 0; sphase ^= 1; }
+          if (++stage == kStages) { stage = 0; sphase ^= 1; }
         }
       }
     }
@@ -173,7 +178,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
             ptx::umma_commit(&tfull[acc]);
           }
           __syncwarp();
-          if (++stage == kFwdStages) { stage = 0; sphase ^= 1; }
+          if (++stage == kStages) { stage = 0; sphase ^= 1; }
           if (++acc == kFwdAcc) { acc = 0; accphase ^= 1; }
         }
         if (ptx::elect_one()) ptx::umma_commit(a_empty);
@@ -212,8 +217,14 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         uint32_t ra[32], rb_[32];
         const float4* wvp = reinterpret_cast<const float4*>(w + (size_t)ct * kBN);   // w_v = 2^a_v of this tile's columns (lane-uniform)
         // stored-E mode: this thread's row of the tile, 16 B (8 columns) at a time, chunk-major inside the 32 KB tile
-        // (offset = chunk * 2048 + row * 16) so that a warp writes 512 contiguous bytes and the backward reads it conflict-free
-        uint8_t* etile = e_store ? e_store + ((size_t)(rb - sch.rb0) * sch.ntiles + ct) * kETileBytes + (size_t)lrow * 16 : nullptr;
+        // (offset = chunk * 2048 + row * 16: conflict-free st.shared here and conflict-free LDS.128 in the backward).  The tile
+        // is staged in this warpgroup's shared-memory buffer and leaves through ONE asynchronous bulk store, so the
+        // exponentiating warps never wait on the global store path.
+        uint8_t* etile = STORE ? sE + (size_t)wg * kETileBytes + (size_t)lrow * 16 : nullptr;
+        if (STORE) {
+          if (quarter == 0 && lane == 0) ptx::bulk_store_wait_read();   // the previous tile's bulk store has read the buffer
+          ptx::named_barrier(2 + wg, 128);
+        }
         auto consume = [&](uint32_t (&r)[32], int c) {
           if (diag) {
 #pragma unroll
@@ -233,9 +244,9 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
             s23 = __ffma2_rn(e23, make_float2(wa.z, wa.w), s23);
             s01 = __ffma2_rn(e45, make_float2(wb.x, wb.y), s01);
             s23 = __ffma2_rn(e67, make_float2(wb.z, wb.w), s23);
-            if (etile)
-              __stcs(reinterpret_cast<uint4*>(etile + (size_t)(c * 4 + (j >> 3)) * 2048),
-                     make_uint4(pack2(e01.x, e01.y), pack2(e23.x, e23.y), pack2(e45.x, e45.y), pack2(e67.x, e67.y)));
+            if (STORE)
+              *reinterpret_cast<uint4*>(etile + (size_t)(c * 4 + (j >> 3)) * 2048) =
+                  make_uint4(pack2(e01.x, e01.y), pack2(e23.x, e23.y), pack2(e45.x, e45.y), pack2(e67.x, e67.y));
           }
         };
         ptx::tmem_ld32(taddr, ra);
@@ -252,10 +263,18 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
         consume(ra, 2);
         consume(rb_, 3);
+        if (STORE) {
+          ptx::fence_proxy_async_smem();          // st.shared -> visible to the bulk-copy (async) proxy
+          ptx::named_barrier(2 + wg, 128);
+          if (quarter == 0 && lane == 0)
+            ptx::bulk_store_1d(e_store + ((size_t)(rb - sch.rb0) * sch.ntiles + ct) * kETileBytes, sE + (size_t)wg * kETileBytes,
+                               (uint32_t)kETileBytes);
+        }
       }
       const int row = rb * kBM + lrow;
       if (row < rows) partial[(size_t)(2 * cc + wg) * rows_padded + row] = (s01.x + s01.y) + (s23.x + s23.y);
     }
+    if (STORE && quarter == 0 && lane == 0) ptx::bulk_store_wait_all();   // shared memory must outlive the last bulk store
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -600,8 +619,9 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 // MMA2 (dZ += P Z_V, A from TMEM, B = the Z_V tile read MN-major) is the only tensor work left.  E_uu was stored as 0, so
 // there is no diagonal handling.  HBM-bound on the E read (32 KB per 8.4 MFLOP tile = 5.3 TB/s at the sustained bf16 rate).
 // TMEM map: [0,256) dZ accumulator, [256,384) / [384,512) P buffers (64 of the 128 columns used, as in the kernel above).
-// smem: 2 stages x (Z_V tile 64 KB + E tile 32 KB).
-constexpr size_t kBwdESmemBytes = 1024 + 2 * ((size_t)kFwdPanelBytes * kMaxPanels + kETileBytes) + 256 + 2 * kBM * sizeof(float);
+// smem: 2 Z_V stages (64 KB each, L2-resident source) + 3 E stages (32 KB each, streamed from HBM).
+constexpr int kBwdEStages = 3;   // E tiles in flight (HBM latency), next to 2 Z_V stages (L2)
+constexpr size_t kBwdESmemBytes = 1024 + 2 * (size_t)kFwdPanelBytes * kMaxPanels + (size_t)kBwdEStages * kETileBytes + 256 + 2 * kBM * sizeof(float);
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -615,12 +635,13 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sB = smem;                          // [2][64 KB] Z_V tiles
-  uint8_t* sE = smem + 2 * kZStage;            // [2][32 KB] E tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + 2 * kETileBytes);
-  uint64_t* full = bars;                    // [2] Z_V tile + E tile landed (transaction bytes)
+  uint8_t* sE = smem + 2 * kZStage;            // [3][32 KB] E tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + kBwdEStages * kETileBytes);
+  uint64_t* full = bars;                    // [2] Z_V tile landed
   uint64_t* empty = full + 2;               // [2] Z_V stage free (MMA2 of its tile retired)
-  uint64_t* e_empty = empty + 2;            // [2] E stage free (8 softmax warps have read it)
-  uint64_t* p_full = e_empty + 2;           // [2][4] P written per 32-column quarter (4 warp arrivals each)
+  uint64_t* e_full = empty + 2;             // [3] E tile landed
+  uint64_t* e_empty = e_full + kBwdEStages; // [3] E stage free (8 softmax warps have read it)
+  uint64_t* p_full = e_empty + kBwdEStages; // [2][4] P written per 32-column quarter (4 warp arrivals each)
   uint64_t* p_empty = p_full + 8;           // [2] P buffer free (MMA2 of its tile retired)
   uint64_t* dz_full = p_empty + 2;
   uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
@@ -634,9 +655,12 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
-      ptx::mbar_init(&e_empty[s], 8);
       ptx::mbar_init(&p_empty[s], 1);
       for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
+    }
+    for (int s = 0; s < kBwdEStages; ++s) {
+      ptx::mbar_init(&e_full[s], 1);
+      ptx::mbar_init(&e_empty[s], 8);
     }
     ptx::mbar_init(dz_full, 1);
     ptx::mbar_init(dz_empty, 8);
@@ -652,18 +676,20 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
   constexpr uint32_t kColS = 256u;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer: Z_V tile (MMA2's B operand) + E tile ----------------
-      uint32_t tcount = 0;
+    if (lane == 0) {  // ---------------- TMA producer: E tile (HBM, 3 deep) + Z_V tile (MMA2's B operand, L2, 2 deep) ----------------
+      uint32_t tcount = 0, es = 0, eph = 0;
       for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         const uint8_t* erow = e_store + (size_t)(rb - rb0) * ntiles * kETileBytes;
         for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
+          ptx::mbar_wait(&e_empty[es], eph ^ 1);
+          ptx::mbar_arrive_expect_tx(&e_full[es], (uint32_t)kETileBytes);
+          ptx::bulk_load_1d(sE + (size_t)es * kETileBytes, erow + (size_t)ct * kETileBytes, (uint32_t)kETileBytes, &e_full[es]);
+          if (++es == kBwdEStages) { es = 0; eph ^= 1; }
           const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
           ptx::mbar_wait(&empty[b], ph ^ 1);
-          ptx::mbar_wait(&e_empty[b], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[b], tile_bytes + (uint32_t)kETileBytes);
+          ptx::mbar_arrive_expect_tx(&full[b], tile_bytes);
           uint8_t* dst = sB + (size_t)b * kZStage;
           for (int p = 0; p < NP; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[b], p * kPanelElems, ct * kBN);
-          ptx::bulk_load_1d(sE + (size_t)b * kETileBytes, erow + (size_t)ct * kETileBytes, (uint32_t)kETileBytes, &full[b]);
         }
       }
     }
@@ -709,7 +735,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
     const int lrow = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
-    uint32_t tcount = 0, dzphase = 0;
+    uint32_t tcount = 0, dzphase = 0, es = 0, eph = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
       const float qu = __ldg(qw + (row >> 1) * 4 + (row & 1)), wu = __ldg(qw + (row >> 1) * 4 + 2 + (row & 1));   // zeros for padding rows
@@ -724,9 +750,9 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
         float4 cvr[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
-        ptx::mbar_wait(&full[b], ph);
+        ptx::mbar_wait(&e_full[es], eph);
         // this thread's row, columns [64 wg, 64 wg + 64): 16-byte chunks 8 wg .. 8 wg + 7 of the chunk-major tile
-        const uint4* ep = reinterpret_cast<const uint4*>(sE + (size_t)b * kETileBytes + (size_t)(wg * 8) * 2048 + (size_t)lrow * 16);
+        const uint4* ep = reinterpret_cast<const uint4*>(sE + (size_t)es * kETileBytes + (size_t)(wg * 8) * 2048 + (size_t)lrow * 16);
         uint4 ev[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ev[i] = ep[i * 128];   // 2048 B apart
@@ -758,7 +784,8 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
         if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + wg]);
         make_p(1, pk);
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&e_empty[b]);   // every lane has consumed its E registers' source: the stage may be refilled
+        if (lane == 0) ptx::mbar_arrive(&e_empty[es]);   // every lane has consumed its E registers' source: the stage may be refilled
+        if (++es == kBwdEStages) { es = 0; eph ^= 1; }
         ptx::tmem_st16(taddr + 16, pk);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -944,10 +971,16 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
   const int n_items = s.nrb * s.nchunks;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
-#define BMKG_LAUNCH_FWD(NP_)                                                                            \
-  {                                                                                                     \
-    if (!set_smem(infonce_fwd_kernel<NP_>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                      \
-    infonce_fwd_kernel<NP_><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, static_cast<uint8_t*>(e_store)); \
+#define BMKG_LAUNCH_FWD(NP_)                                                                                          \
+  {                                                                                                                   \
+    if (e_store) {                                                                                                    \
+      if (!set_smem(infonce_fwd_kernel<NP_, true>, kFwdSmemBytesStore)) return BMKG_ERR_LAUNCH;                       \
+      infonce_fwd_kernel<NP_, true><<<grid, kThreads, kFwdSmemBytesStore, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, \
+                                                                                static_cast<uint8_t*>(e_store));      \
+    } else {                                                                                                          \
+      if (!set_smem(infonce_fwd_kernel<NP_, false>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                           \
+      infonce_fwd_kernel<NP_, false><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, nullptr); \
+    }                                                                                                                 \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_FWD(1) break;

@@ -102,6 +102,9 @@ class CudaImpl:
         if r1 > r0:
             call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), _p(getattr(self, "e_store", None)), N, B, D, r0, r1,
                  dz.data_ptr() - r0 * D * 4, _stream())
+            from .ops import release_e_store
+
+            release_e_store(getattr(self, "e_store", None))
             self.e_store = None
         return dz
 

@@ -715,6 +715,7 @@ class _InfoNCEFn(torch.autograd.Function):
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
         call("bmkg_infonce_bwd", _p(z), _p(qw), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _stream())
+        release_e_store(e_store)
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())
         call("bmkg_l2norm_scale_bwd", _p(h2), inv_norm.data_ptr() + N * 4, dz.data_ptr() + N * D * 4, N, D, ctx.scale, _p(dh2),
@@ -742,7 +743,29 @@ def alloc_e_store(N, B, r0, r1, device):
         free, _ = torch.cuda.mem_get_info(device)
         cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)      # reusable without a new device allocation
         ok = _E_STORE_DECISION[key] = need <= min(E_STORE_MAX_BYTES, E_STORE_FREE_FRACTION * (free + cached))
-    return torch.empty(need, dtype=torch.uint8, device=device) if ok else None
+    if not ok:
+        return None
+    # Buffers live in a small pool instead of going back to torch's caching allocator after every backward: the allocator may
+    # split a freed multi-GB block to serve small requests, and the next step's request for the full size would then need a
+    # second device allocation (cfg4 on one GPU: 126 GiB - there is no room for two).
+    pool = _E_STORE_POOL.setdefault(key, [])
+    return pool.pop() if pool else torch.empty(need, dtype=torch.uint8, device=device)
+
+
+_E_STORE_POOL: dict = {}
+
+
+def release_e_store(buf):
+    """Hand an E store back after the backward that read it (a buffer whose backward never runs is simply garbage-collected)."""
+    if buf is not None and E_STORE_FREE_FRACTION > 0:
+        pool = _E_STORE_POOL.setdefault((buf.numel(), buf.device.index), [])
+        if len(pool) < 2:
+            pool.append(buf)
+
+
+def drop_e_store_pool():
+    _E_STORE_POOL.clear()
+    _E_STORE_DECISION.clear()
 
 
 #: centre the InfoNCE operand on its column mean (False = plain bf16 rows, mu = 0; only for A/B numerics tests)
