@@ -79,6 +79,10 @@ SIGNATURES = {
     "bmkg_redaf_fwd": (I, [P, P, P, I64, I, I, F, U64, P, P, P]),
     "bmkg_redaf_bwd": (I, [P, P, P, P, I64, I, I, F, U64, P, P, P, P]),
     "bmkg_colsum_bf16": (I, [P, P, P, I64, I, I, P, P, P, SZ, P]),
+    "bmkg_linear_supported": (I, [I64, I, I]),
+    "bmkg_linear_nt": (I, [P, P, P, I64, I, I, I, I, P, P, P, I, P, P, P]),
+    "bmkg_linear_tn_workspace_bytes": (SZ, [I64, I, I]),
+    "bmkg_linear_tn": (I, [P, P, P, I64, I, I, P, P, SZ, P]),
     "bmkg_infonce_stacked_rows": (I64, [I64, I64]),
     "bmkg_infonce_padded_rows": (I64, [I64, I64]),
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
@@ -123,7 +127,7 @@ def bind_thread(device_index: int) -> None:
 KERNELS_PER_CALL = {
     "bmkg_edge_sort": None,            # data dependent: 3 + 5 * passes + 2 (counted by formula in bench.py)
     "bmkg_csr_filter": 6, "bmkg_gcn_aggregate": 1, "bmkg_gcn_aggregate_rows": 1, "bmkg_gcn_star_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
-    "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_center_cast": 1, "bmkg_l2norm_colsum": 2, "bmkg_center_scale": 1, "bmkg_l2norm_scale_bwd": 1,
+    "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_linear_nt": 1, "bmkg_linear_tn": 2, "bmkg_center_cast": 1, "bmkg_l2norm_colsum": 2, "bmkg_center_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
     "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
     "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,

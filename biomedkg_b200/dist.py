@@ -290,8 +290,8 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
         g_full = _all_gather_rows(gpre, num_nodes, block, group).contiguous()
         hub = view.hub_csc if view.hub_possible else None
         dxw = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, g_full, hub_rows=hub, row_range=(r0, r1))
-        dw = ops._mm_f32(dxw.t(), x_loc) if ctx.needs_input_grad[1] else None
-        dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm_tn(dxw, x_loc) if ctx.needs_input_grad[1] else None
+        dx = ops.gemm_nt(dxw, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
         return (dx, dw, dbias) + (None,) * 12
 
 

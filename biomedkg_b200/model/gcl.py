@@ -38,7 +38,7 @@ class GRACE(nn.Module):
         return z, z1, z2
 
     def project(self, z: torch.Tensor) -> torch.Tensor:
-        h = F.elu(ops.centered_linear(z, self.fc1.weight, self.fc1.bias))
+        h = ops.centered_linear(z, self.fc1.weight, self.fc1.bias, elu=True)      # F.elu fused into the GEMM epilogue
         return ops.centered_linear(h, self.fc2.weight, self.fc2.bias)
 
 

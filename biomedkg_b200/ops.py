@@ -43,11 +43,71 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 
 
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """bf16 x bf16 -> fp32 (fp32 accumulate, no bf16 rounding of the result)."""
+    """bf16 x bf16 -> fp32 (fp32 accumulate, no bf16 rounding of the result) - library GEMM, only for shapes the tcgen05
+    kernels do not take (``gemm_nt`` / ``gemm_tn`` below)."""
     try:
         return torch.mm(a, b, out_dtype=torch.float32)
     except TypeError:  # older torch: no out_dtype
         return torch.mm(a, b).float()
+
+
+#: calls that fell back to the library GEMM because of an unsupported shape (N % 16, K % 64); tests assert it stays 0 for the
+#: BASELINE configurations
+library_gemm_calls = 0
+
+
+def gemm_nt(a16, b16, bias=None, elu=False, out_f32=False, gat=None):
+    """C[M,N] = A[M,K] B[N,K]^T (+ bias) (ELU) on the hand-written tcgen05 kernel (csrc/gemm.cu).  A, B bf16 contiguous; bias
+    fp32 [N].  ``gat=(att_src, att_dst, heads)`` (fp32 flat [N]) also returns the GATConv node scores (a_src, a_dst) [M, heads]
+    computed in the epilogue from the bf16-rounded row."""
+    global library_gemm_calls
+    M, K = a16.shape
+    N = b16.size(0)
+    dev = a16.device
+    if M == 0 or not lib.bmkg_linear_supported(M, N, K) or (gat is not None and (N > 256 or out_f32)):
+        library_gemm_calls += 1
+        y = _mm_f32(a16, b16.t())
+        if bias is not None:
+            y = y + bias
+        if elu:
+            y = torch.nn.functional.elu(y)
+        y = y if out_f32 else y.to(BF16)
+        if gat is None:
+            return y
+        a_s = torch.empty(M, gat[2], dtype=torch.float32, device=dev)
+        a_d = torch.empty(M, gat[2], dtype=torch.float32, device=dev)
+        if M > 0:
+            call("bmkg_gat_scores", _p(y), _p(gat[0]), _p(gat[1]), M, gat[2], N // gat[2], _p(a_s), _p(a_d), _stream())
+        return y, a_s, a_d
+    a16, b16 = a16.contiguous(), b16.contiguous()
+    out = torch.empty(M, N, dtype=torch.float32 if out_f32 else BF16, device=dev)
+    b = None if bias is None else bias.detach().float().contiguous()
+    if gat is None:
+        call("bmkg_linear_nt", _p(a16), _p(b16), _p(b), M, N, K, int(elu), int(out_f32), _p(out), None, None, 1, None, None, _stream())
+        return out
+    a_s = torch.empty(M, gat[2], dtype=torch.float32, device=dev)
+    a_d = torch.empty(M, gat[2], dtype=torch.float32, device=dev)
+    call("bmkg_linear_nt", _p(a16), _p(b16), _p(b), M, N, K, int(elu), 0, _p(out), _p(gat[0]), _p(gat[1]), int(gat[2]), _p(a_s), _p(a_d),
+         _stream())
+    return out, a_s, a_d
+
+
+def gemm_tn(g16, x16, addend=None):
+    """C[N,K] = sum_m G[m,N] X[m,K] (+ addend) in fp32 - the weight gradient dW = dY^T X, reduced over the node dimension on
+    the tensor cores from the row-major operands as they are (MN-major tiles), split over CTAs with a fixed-order combine."""
+    global library_gemm_calls
+    M, N = g16.shape
+    K = x16.size(1)
+    if M == 0 or N % 8 or K % 64 or K < 64:
+        library_gemm_calls += 1
+        y = _mm_f32(g16.t(), x16) if M > 0 else torch.zeros(N, K, dtype=torch.float32, device=g16.device)
+        return y if addend is None else y + addend
+    g16, x16 = g16.contiguous(), x16.contiguous()
+    out = torch.empty(N, K, dtype=torch.float32, device=g16.device)
+    ws = _ws(lib.bmkg_linear_tn_workspace_bytes(M, N, K), g16.device)
+    ad = None if addend is None else addend.float().contiguous()
+    call("bmkg_linear_tn", _p(g16), _p(x16), _p(ad), M, N, K, _p(out), _p(ws), ws.numel(), _stream())
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -303,14 +363,7 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, out_bf16):
         x16 = x if x.dtype == BF16 else x.to(BF16)
         w16 = weight.to(BF16)
-        if out_bf16:
-            y = torch.mm(x16, w16.t())
-            if bias is not None:
-                y = y + bias.to(BF16)
-        else:
-            y = _mm_f32(x16, w16.t())
-            if bias is not None:
-                y = y + bias
+        y = gemm_nt(x16, w16, bias, out_f32=not out_bf16)        # bias added in fp32 in the epilogue, before any rounding
         ctx.save_for_backward(x16, w16)
         ctx.has_bias = bias is not None
         ctx.x_dtype = x.dtype
@@ -320,8 +373,8 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, g):
         x16, w16 = ctx.saved_tensors
         g16 = g.contiguous() if g.dtype == BF16 else g.to(BF16)
-        dx = torch.mm(g16, w16).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
-        dw = _mm_f32(g16.t(), x16) if ctx.needs_input_grad[1] else None
+        dx = gemm_nt(g16, w16.t().contiguous()).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(g16, x16) if ctx.needs_input_grad[1] else None
         db = _colsum_any(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
@@ -339,7 +392,7 @@ class _CenteredLinearFn(torch.autograd.Function):
     plain bf16 cast of x would erase exactly the part the contrastive gradient depends on (DESIGN.md "Centred bf16 operands")."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, elu):
         _need_cuda(x)
         x = x.contiguous().float()
         N, K = x.shape
@@ -350,41 +403,46 @@ class _CenteredLinearFn(torch.autograd.Function):
         shift = torch.mv(weight.float(), m)
         if bias is not None:
             shift = shift + bias
-        y = _mm_f32(xc16, w16.t()) + shift
-        ctx.save_for_backward(xc16, w16, m)
+        y = gemm_nt(xc16, w16, shift, elu=elu, out_f32=True)       # fp32 rank-1 term + bias (+ ELU) in the GEMM epilogue
+        ctx.save_for_backward(xc16, w16, m, y if elu else None)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
-        xc16, w16, m = ctx.saved_tensors
+        xc16, w16, m, y = ctx.saved_tensors
         g = g.contiguous()
+        if y is not None:                                            # ELU'(pre) = 1 if pre > 0 else exp(pre) = y + 1
+            g = torch.where(y > 0, g, g * (y + 1.0))
         g16 = g if g.dtype == BF16 else g.to(BF16)
         db = _colsum_any(g)
-        dx = _mm_f32(g16, w16) if ctx.needs_input_grad[0] else None      # fp32 out: its column sums (bias gradients upstream) cancel heavily
-        dw = torch.addmm(_mm_f32(g16.t(), xc16), db.unsqueeze(1), m.unsqueeze(0)) if ctx.needs_input_grad[1] else None   # g^T (xc + 1 m^T)
-        return dx, dw, (db if ctx.has_bias and ctx.needs_input_grad[2] else None)
+        # fp32 out: the column sums of dx (bias gradients upstream) cancel heavily
+        dx = gemm_nt(g16, w16.t().contiguous(), out_f32=True) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(g16, xc16, addend=torch.outer(db, m)) if ctx.needs_input_grad[1] else None        # g^T (xc + 1 m^T)
+        return dx, dw, (db if ctx.has_bias and ctx.needs_input_grad[2] else None), None
 
 
-def centered_linear(x, weight, bias=None):
-    if x.numel() % 4 or x.shape[-1] % 4:
-        return linear(x, weight, bias)
-    return _CenteredLinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias)
+def centered_linear(x, weight, bias=None, elu=False):
+    if x.numel() % 4 or x.shape[-1] % 4 or x.shape[0] == 0:
+        y = linear(x, weight, bias)
+        return torch.nn.functional.elu(y) if elu else y
+    return _CenteredLinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias, bool(elu))
 
 
 #: add the rank-1 fp32 correction  mean(x) (W - bf16(W))^T  to the conv layers' X W^T (False only for A/B numerics tests)
 WEIGHT_RESIDUAL = True
 
 
-def _xw(x16, weight, w16, correct):
-    """X W^T on the tensor cores with bf16 operands.  ``correct``: the layer input is an activation whose rows share a common
-    component m = colmean(x); the rounding of W then shifts every output row by the same vector m (W - bf16 W)^T, which is
-    restored in fp32 through the GEMM's bias epilogue (one [K] column mean + one [C,K] GEMV)."""
-    if not (correct and WEIGHT_RESIDUAL) or x16.size(1) % 8:
-        return torch.mm(x16, w16.t())
-    m = colsum_bf16(x16)[0] / x16.size(0)
-    dc = torch.mv(weight.detach().float() - w16.float(), m)
-    return torch.addmm(dc.to(BF16), x16, w16.t())
+def _xw(x16, weight, w16, correct, gat=None):
+    """X W^T on the tensor cores with bf16 operands (csrc/gemm.cu).  ``correct``: the layer input is an activation whose rows
+    share a common component m = colmean(x); the rounding of W then shifts every output row by the same vector
+    m (W - bf16 W)^T, which is restored in fp32 through the GEMM's bias epilogue (one [K] column mean + one [C,K] GEMV).
+    ``gat``: see gemm_nt (fused GATConv node scores)."""
+    dc = None
+    if correct and WEIGHT_RESIDUAL and x16.size(1) % 8 == 0 and x16.size(0) > 0:
+        m = colsum_bf16(x16)[0] / x16.size(0)
+        dc = torch.mv(weight.detach().float() - w16.float(), m)
+    return gemm_nt(x16, w16, dc, gat=gat)
 
 
 # ---------------------------------------------------------------------------
@@ -427,8 +485,8 @@ class _GCNLayerFn(torch.autograd.Function):
             dbias = colsum(gy.float())
             gpre = gy if gy.dtype == BF16 else gy.to(BF16)
         dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub_csc if view.hub_possible else None)
-        dw = _mm_f32(dxw.t(), x) if ctx.needs_input_grad[1] else None
-        dx = torch.mm(dxw, w16) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(dxw, x) if ctx.needs_input_grad[1] else None
+        dx = gemm_nt(dxw, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, None, None, None, None, None, None, None
 
 
@@ -456,12 +514,9 @@ class _GATLayerFn(torch.autograd.Function):
         C = HC // heads
         dev = x.device
         w16 = weight.to(BF16)
-        xh = _xw(x, weight, w16, correct)
         atts = att_src.detach().reshape(-1).float().contiguous()
         attd = att_dst.detach().reshape(-1).float().contiguous()
-        a_s = torch.empty(N, heads, dtype=torch.float32, device=dev)
-        a_d = torch.empty(N, heads, dtype=torch.float32, device=dev)
-        call("bmkg_gat_scores", _p(xh), _p(atts), _p(attd), N, heads, C, _p(a_s), _p(a_d), _stream())
+        xh, a_s, a_d = _xw(x, weight, w16, correct, gat=(atts, attd, heads))     # node scores from the GEMM epilogue
         out = torch.empty(N, HC, dtype=torch.float32 if out_fp32 else BF16, device=dev)
         rmax = torch.empty(N, heads, dtype=torch.float32, device=dev)
         rsum = torch.empty(N, heads, dtype=torch.float32, device=dev)
@@ -506,8 +561,8 @@ class _GATLayerFn(torch.autograd.Function):
              _p(tsum), cap, _p(view.hub_csr), _p(view.hub_csc), _p(hws), hws.numel() if hws is not None else 0, _stream())
         datt_s, datt_d = colsum_bf16(xh, das, dad, H)          # d att_src[h,c] = sum_n d a_src[n,h] xh[n,h,c]
         datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
-        dw = _mm_f32(dxh.t(), x) if ctx.needs_input_grad[1] else None
-        dx = torch.mm(dxh, w16) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(dxh, x) if ctx.needs_input_grad[1] else None
+        dx = gemm_nt(dxh, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
         return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None, None
 
 
@@ -725,9 +780,12 @@ class _InfoNCEFn(torch.autograd.Function):
 
 #: Stored-E backward (csrc/infonce.cu): the forward keeps E = 2^S as bf16 (8 N^2 bytes for a full launch) so the backward does
 #: not recompute the similarities.  Used when the buffer fits in this fraction of the currently free device memory (and under
-#: the absolute cap, bytes); 0 disables it (the recomputing backward).  A fixed-shape training loop allocates the buffer from
-#: torch's caching allocator every step, i.e. without a device allocation after the first.
-E_STORE_FREE_FRACTION = float(_os.environ.get("BMKG_E_STORE_FRACTION", "0.8"))
+#: the absolute cap, bytes); 0 disables it (the recomputing backward).
+#: DEFAULT OFF: measured on B200 (profiles/r2_infonce_stored_e.md) the backward drops from 2.34 to 1.72 ms at N = 28k (0.51 ->
+#: 0.68 of the sustained bf16 rate on the credited 8 N^2 D), but the forward then writes 8 N^2 bytes at the ~3.3 TB/s the HBM
+#: write path sustains (1.0 -> 2.0 ms), so forward + backward end up slower (3.7 vs 3.3 ms).  Kept as a tested option
+#: (BMKG_E_STORE_FRACTION=0.8) for configurations whose forward is not on the critical path.
+E_STORE_FREE_FRACTION = float(_os.environ.get("BMKG_E_STORE_FRACTION", "0"))
 E_STORE_MAX_BYTES = int(float(_os.environ.get("BMKG_E_STORE_MAX_GB", "150")) * 2**30)
 _E_STORE_DECISION: dict = {}
 

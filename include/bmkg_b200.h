@@ -217,6 +217,23 @@ int bmkg_redaf_bwd(const void* t_bf16, const float* bias, const float* gate, con
                    int embed, float drop_p, uint64_t drop_seed, const uint8_t* drop_keep, void* dt_bf16, float* dgate_partial,
                    void* stream);
 
+/* ---- L1: Linear layers on tcgen05 (bf16 operands, fp32 accumulate in TMEM, TMA-fed) --------------------
+ * torch.nn.Linear / PyG Linear y = x W^T + b at biomedkg/utils/fusion.py:18-20,70 (q/k/v and ReDAF projections),
+ * biomedkg/model/encoder.py:138-143 (GCNConv.lin) and biomedkg/model/gcl.py:49-51 (GRACE.project).
+ * bmkg_linear_nt: C[M,N] = A[M,K] B[N,K]^T (+ bias[N] fp32) (then ELU if elu); A, B bf16 row-major; C bf16 or fp32 (out_f32).
+ *   Forward: B = W [out,in].  Input gradient: A = dY, B = W^T [in,out] (transposed by the caller).  N % 16 == 0, K % 64 == 0
+ *   (bmkg_linear_supported).  Optional GAT epilogue (att_src != NULL; N = heads*channels <= 256, bf16 output): also writes
+ *   a_src[m,h] = <bf16 row m, head h, att_src[h]>, a_dst likewise - the node scores of PyG GATConv (replaces bmkg_gat_scores).
+ * bmkg_linear_tn: C[N,K] = sum_m G[m,N] X[m,K] (+ addend[N,K] fp32) - the weight gradient dW = dY^T X, fp32 out; the node range is
+ *   split over CTAs and the partial tiles are added in fixed order (deterministic).  N % 8 == 0, K % 64 == 0. */
+int bmkg_linear_supported(int64_t rows, int out_features, int in_features);
+int bmkg_linear_nt(const void* a_bf16, const void* b_bf16, const float* bias, int64_t rows, int out_features, int in_features, int elu,
+                   int out_f32, void* out, const float* att_src, const float* att_dst, int heads, float* a_src, float* a_dst,
+                   void* stream);
+size_t bmkg_linear_tn_workspace_bytes(int64_t rows, int out_features, int in_features);
+int bmkg_linear_tn(const void* g_bf16, const void* x_bf16, const float* addend, int64_t rows, int out_features, int in_features,
+                   float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- I1/I2: fused GRACE InfoNCE (tcgen05 / TMEM / TMA) -----------------------------------
  * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).
  * Operand (bmkg_center_scale): z bf16 [R, D] holds the DEVIATIONS d_u of the normalised, sqrt(log2e/tau)-scaled rows from a

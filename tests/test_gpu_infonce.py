@@ -233,10 +233,15 @@ def test_infonce_cluster_closed_form_large_n(n):
     R = (nc - 1.0) * math.exp(1.0 / tau) + (2.0 * n - nc)                      # exact-arithmetic value: the stated tolerance
     exact = float((torch.log(R) * nc).sum() / (2.0 * n) - 1.0 / tau)
     assert abs(float(loss) - exact) <= 1e-3 * abs(exact)
-    # gradient the device's operand implies (same K-cluster collapse): dz_c = ln2/2N [sum_c' n_c' P_cc' zt_c' - P_cc zt_c - 2 zt_c],
-    # P_cc' = 2^G_cc' (1/R_c + 1/R_c'), then the normalisation backward dh_u = s (dz_c - e_c dz_c[c]) (|h_u| = 1)
+    # gradient the device's data flow implies (same K-cluster collapse), INCLUDING its bf16 P: every same-cluster-pair entry of
+    # P is the same number, so its rounding is coherent here (5e-3 of the gradient on its own) instead of averaging out:
+    #   dz_c = ln2/2N [sum_c' n_c' bf16(P_cc') d_c' - bf16(P_cc) d_c + mu (sum_v P_cv - 2) - 2 zt_c],  P_cc' = 2^G_cc' (1/R_c + 1/R_c'),
+    # then the normalisation backward dh_u = s (dz_c - e_c dz_c[c]) (|h_u| = 1)
     P = torch.exp2(G) * (1.0 / Rk[:, None] + 1.0 / Rk[None, :])
-    dzk = (math.log(2.0) / (2.0 * n)) * ((P * nc[None, :]) @ zt - torch.diagonal(P)[:, None] * zt - 2.0 * zt)
+    Pr, dd = P.to(torch.bfloat16).double(), dev_rows.double()
+    rowsum = (P * nc[None, :]).sum(1) - torch.diagonal(P)
+    dzk = (math.log(2.0) / (2.0 * n)) * ((Pr * nc[None, :]) @ dd - torch.diagonal(Pr)[:, None] * dd
+                                         + (rowsum - 2.0)[:, None] * mu.double()[None, :] - 2.0 * dd)
     dzk[torch.arange(K), torch.arange(K)] = 0.0                                # minus the component along h_u = e_c
     gdev = (float(s32) * dzk)[c]
     # ... and the exact-arithmetic gradient (no rounding anywhere)
