@@ -256,15 +256,15 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
     def forward(ctx, x_loc, weight, bias, view, r0, r1, num_nodes, block, group, relu, drop_p, drop_seed, drop_keep, out_fp32, correct):
         from . import ops
 
-        w16 = weight.to(torch.bfloat16)
+        w16t = ops.weight_forms(weight)[1]
         # the weight-residual correction uses the mean of the LOCAL rows: any common vector restores the rounded-away part
-        xw_loc = ops._xw(x_loc, weight, w16, correct and x_loc.size(0) > 0)
+        xw_loc = ops._xw(x_loc, weight, correct and x_loc.size(0) > 0)
         xw = _all_gather_rows(xw_loc, num_nodes, block, group).contiguous()
         hub = view.hub_csr if view.hub_possible else None
         y = ops.gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
                               hub_rows=hub, row_range=(r0, r1))
         ctx.meta = (view, r0, r1, num_nodes, block, group, relu, drop_p)
-        ctx.save_for_backward(x_loc, w16, y if relu else None)
+        ctx.save_for_backward(x_loc, w16t, y if relu else None)
         return y
 
     @staticmethod
@@ -272,7 +272,7 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
         from . import ops
         from .ops import _p, _stream, _ws, call, lib
 
-        x_loc, w16, y = ctx.saved_tensors
+        x_loc, w16t, y = ctx.saved_tensors
         view, r0, r1, num_nodes, block, group, relu, drop_p = ctx.meta
         gy = gy.contiguous()
         n, C = gy.shape
@@ -291,7 +291,7 @@ class _ShardedGCNLayerFn(torch.autograd.Function):
         hub = view.hub_csc if view.hub_possible else None
         dxw = ops.gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, g_full, hub_rows=hub, row_range=(r0, r1))
         dw = ops.gemm_tn(dxw, x_loc) if ctx.needs_input_grad[1] else None
-        dx = ops.gemm_nt(dxw, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dx = ops.gemm_nt(dxw, w16t) if ctx.needs_input_grad[0] else None
         return (dx, dw, dbias) + (None,) * 12
 
 

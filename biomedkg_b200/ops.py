@@ -51,6 +51,30 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return torch.mm(a, b).float()
 
 
+_WEIGHT_FORMS: dict = {}
+
+
+def weight_forms(weight):
+    """(bf16 W, bf16 W^T contiguous, fp32 W - bf16 W) of a parameter, computed once per parameter VERSION (an optimiser step or a
+    load_state_dict bumps ``_version``) instead of once per GEMM call: a GRACE step calls every conv layer's GEMMs three times
+    forward and twice backward.  Bypassed while a CUDA graph is being captured - a captured step must contain its own casts,
+    or its replays would keep reading the weights of the capture."""
+    import weakref
+
+    w = weight.detach()
+    if not w.is_cuda or torch.cuda.is_current_stream_capturing():
+        w16 = w.to(BF16)
+        return w16, w16.t().contiguous(), w.float() - w16.float()
+    key = id(weight)
+    ent = _WEIGHT_FORMS.get(key)
+    if ent is None or ent[0]() is not weight or ent[1] != weight._version or ent[2] != w.data_ptr():
+        w16 = w.to(BF16)
+        if len(_WEIGHT_FORMS) > 256:
+            _WEIGHT_FORMS.clear()
+        ent = _WEIGHT_FORMS[key] = (weakref.ref(weight), weight._version, w.data_ptr(), w16, w16.t().contiguous(), w.float() - w16.float())
+    return ent[3], ent[4], ent[5]
+
+
 #: calls that fell back to the library GEMM because of an unsupported shape (N % 16, K % 64); tests assert it stays 0 for the
 #: BASELINE configurations
 library_gemm_calls = 0
@@ -362,18 +386,18 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, out_bf16):
         x16 = x if x.dtype == BF16 else x.to(BF16)
-        w16 = weight.to(BF16)
+        w16, w16t, _ = weight_forms(weight)
         y = gemm_nt(x16, w16, bias, out_f32=not out_bf16)        # bias added in fp32 in the epilogue, before any rounding
-        ctx.save_for_backward(x16, w16)
+        ctx.save_for_backward(x16, w16t)
         ctx.has_bias = bias is not None
         ctx.x_dtype = x.dtype
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x16, w16 = ctx.saved_tensors
+        x16, w16t = ctx.saved_tensors
         g16 = g.contiguous() if g.dtype == BF16 else g.to(BF16)
-        dx = gemm_nt(g16, w16.t().contiguous()).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        dx = gemm_nt(g16, w16t).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
         dw = gemm_tn(g16, x16) if ctx.needs_input_grad[1] else None
         db = _colsum_any(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
@@ -399,25 +423,25 @@ class _CenteredLinearFn(torch.autograd.Function):
         m = colsum(x) / N
         xc16 = torch.empty(N, K, dtype=BF16, device=x.device)
         call("bmkg_center_cast", _p(x), _p(m), N, K, _p(xc16), _stream())
-        w16 = weight.to(BF16)
-        shift = torch.mv(weight.float(), m)
+        w16, w16t, _ = weight_forms(weight)
+        shift = torch.mv(weight.detach().float(), m)
         if bias is not None:
             shift = shift + bias
         y = gemm_nt(xc16, w16, shift, elu=elu, out_f32=True)       # fp32 rank-1 term + bias (+ ELU) in the GEMM epilogue
-        ctx.save_for_backward(xc16, w16, m, y if elu else None)
+        ctx.save_for_backward(xc16, w16t, m, y if elu else None)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
-        xc16, w16, m, y = ctx.saved_tensors
+        xc16, w16t, m, y = ctx.saved_tensors
         g = g.contiguous()
         if y is not None:                                            # ELU'(pre) = 1 if pre > 0 else exp(pre) = y + 1
             g = torch.where(y > 0, g, g * (y + 1.0))
         g16 = g if g.dtype == BF16 else g.to(BF16)
         db = _colsum_any(g)
         # fp32 out: the column sums of dx (bias gradients upstream) cancel heavily
-        dx = gemm_nt(g16, w16.t().contiguous(), out_f32=True) if ctx.needs_input_grad[0] else None
+        dx = gemm_nt(g16, w16t, out_f32=True) if ctx.needs_input_grad[0] else None
         dw = gemm_tn(g16, xc16, addend=torch.outer(db, m)) if ctx.needs_input_grad[1] else None        # g^T (xc + 1 m^T)
         return dx, dw, (db if ctx.has_bias and ctx.needs_input_grad[2] else None), None
 
@@ -433,15 +457,15 @@ def centered_linear(x, weight, bias=None, elu=False):
 WEIGHT_RESIDUAL = True
 
 
-def _xw(x16, weight, w16, correct, gat=None):
+def _xw(x16, weight, correct, gat=None):
     """X W^T on the tensor cores with bf16 operands (csrc/gemm.cu).  ``correct``: the layer input is an activation whose rows
     share a common component m = colmean(x); the rounding of W then shifts every output row by the same vector
     m (W - bf16 W)^T, which is restored in fp32 through the GEMM's bias epilogue (one [K] column mean + one [C,K] GEMV).
     ``gat``: see gemm_nt (fused GATConv node scores)."""
+    w16, _, resid = weight_forms(weight)
     dc = None
     if correct and WEIGHT_RESIDUAL and x16.size(1) % 8 == 0 and x16.size(0) > 0:
-        m = colsum_bf16(x16)[0] / x16.size(0)
-        dc = torch.mv(weight.detach().float() - w16.float(), m)
+        dc = torch.mv(resid, colsum_bf16(x16)[0]) / x16.size(0)
     return gemm_nt(x16, w16, dc, gat=gat)
 
 
@@ -460,17 +484,17 @@ class _GCNLayerFn(torch.autograd.Function):
         if relu and out_fp32:
             raise ValueError("relu=True needs out_fp32=False: the ReLU/dropout backward re-reads the saved bf16 output")
         x = x.contiguous()
-        w16 = weight.to(BF16)
-        xw = _xw(x, weight, w16, correct)
+        w16t = weight_forms(weight)[1]
+        xw = _xw(x, weight, correct)
         y = gcn_aggregate(view.rowptr, view.colind, view.dis, xw, bias.contiguous(), relu, drop_p, drop_seed, drop_keep, out_fp32,
                           hub_rows=view.hub_csr if view.hub_possible else None)
         ctx.view, ctx.relu, ctx.drop_p = view, relu, drop_p
-        ctx.save_for_backward(x, w16, y if relu else None)
+        ctx.save_for_backward(x, w16t, y if relu else None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w16, y = ctx.saved_tensors
+        x, w16t, y = ctx.saved_tensors
         view = ctx.view
         gy = gy.contiguous()
         N, C = gy.shape
@@ -486,7 +510,7 @@ class _GCNLayerFn(torch.autograd.Function):
             gpre = gy if gy.dtype == BF16 else gy.to(BF16)
         dxw = gcn_aggregate(view.csc_rowptr, view.csc_colind, view.dis, gpre, hub_rows=view.hub_csc if view.hub_possible else None)
         dw = gemm_tn(dxw, x) if ctx.needs_input_grad[1] else None
-        dx = gemm_nt(dxw, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dx = gemm_nt(dxw, w16t) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, None, None, None, None, None, None, None
 
 
@@ -513,10 +537,10 @@ class _GATLayerFn(torch.autograd.Function):
         HC = weight.size(0)
         C = HC // heads
         dev = x.device
-        w16 = weight.to(BF16)
+        w16t = weight_forms(weight)[1]
         atts = att_src.detach().reshape(-1).float().contiguous()
         attd = att_dst.detach().reshape(-1).float().contiguous()
-        xh, a_s, a_d = _xw(x, weight, w16, correct, gat=(atts, attd, heads))     # node scores from the GEMM epilogue
+        xh, a_s, a_d = _xw(x, weight, correct, gat=(atts, attd, heads))     # node scores from the GEMM epilogue
         out = torch.empty(N, HC, dtype=torch.float32 if out_fp32 else BF16, device=dev)
         rmax = torch.empty(N, heads, dtype=torch.float32, device=dev)
         rsum = torch.empty(N, heads, dtype=torch.float32, device=dev)
@@ -529,12 +553,12 @@ class _GATLayerFn(torch.autograd.Function):
              cap, _p(view.hub_csr), _p(hws), hws.numel() if hws is not None else 0, _stream())
         ctx.view, ctx.relu, ctx.drop_p, ctx.heads, ctx.slope = view, relu, drop_p, heads, slope
         ctx.att_shape = att_src.shape
-        ctx.save_for_backward(x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, out if relu else None)
+        ctx.save_for_backward(x, w16t, xh, a_s, a_d, rmax, rsum, atts, attd, out if relu else None)
         return out
 
     @staticmethod
     def backward(ctx, gy):
-        x, w16, xh, a_s, a_d, rmax, rsum, atts, attd, y = ctx.saved_tensors
+        x, w16t, xh, a_s, a_d, rmax, rsum, atts, attd, y = ctx.saved_tensors
         view, H = ctx.view, ctx.heads
         gy = gy.contiguous()
         N, HC = gy.shape
@@ -562,7 +586,7 @@ class _GATLayerFn(torch.autograd.Function):
         datt_s, datt_d = colsum_bf16(xh, das, dad, H)          # d att_src[h,c] = sum_n d a_src[n,h] xh[n,h,c]
         datt_s, datt_d = datt_s.reshape(ctx.att_shape), datt_d.reshape(ctx.att_shape)
         dw = gemm_tn(dxh, x) if ctx.needs_input_grad[1] else None
-        dx = gemm_nt(dxh, w16.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dx = gemm_nt(dxh, w16t) if ctx.needs_input_grad[0] else None
         return dx, dw, datt_s, datt_d, dbias, None, None, None, None, None, None, None, None, None
 
 
