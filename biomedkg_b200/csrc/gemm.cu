@@ -371,7 +371,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols
 
 static int tn_splits(int64_t M, int tiles) {
   int s = (2 * kNumSMs) / (tiles > 0 ? tiles : 1);
-  const int64_t max_by_rows = ceil_div(M, 4 * kTnRows);   // at least 256 rows per split
+  const int64_t max_by_rows = ceil_div(M, 16 * kTnRows);   // at least 1024 rows per split: the partial tiles cost N*K*4 bytes each
   if (s > max_by_rows) s = (int)max_by_rows;
   return s < 1 ? 1 : s;
 }

@@ -259,7 +259,7 @@ def test_infonce_cluster_closed_form_large_n(n):
         tol = 4e-3 if n < 100_000 else 1.5e-2
         assert rel_err(got, gdev) < tol, rel_err(got, gdev)
         row_err = (got.double().cpu() - gdev).norm(dim=1) / gdev.norm(dim=1)
-        assert float(row_err.max()) < 2.5 * tol                                # every row, not just on average
+        assert float(row_err.max()) < (1e-2 if n < 100_000 else 6e-2)          # every row, not just on average (worst: the smallest clusters)
         # against exact arithmetic this input is the format's worst case: all rows of a cluster are the SAME vector, so the
         # bf16 rounding of its one large component (up to 2^-9 of 2.7) shifts a whole block of similarities coherently
         # (up to 0.03 in log2 units = 2 % of 2^S) instead of averaging out as it does for generic rows
