@@ -345,12 +345,41 @@ def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
     x0, x1, x2 = ops.mask_cast(fused.float().contiguous(), m1[r0:r1].contiguous(), m2[r0:r1].contiguous(),
                                want_plain=not model.skip_unused_view)
     enc = model.encoder
+    views = [(x1, sg.view(k1)), (x2, sg.view(k2))]
     if not model.skip_unused_view:
-        sharded_gcn_encoder(enc, x0, sg.view(None), r0, r1, N, block, group)   # the reference's unused un-augmented view
-    z1 = sharded_gcn_encoder(enc, x1, sg.view(k1), r0, r1, N, block, group)
-    z2 = sharded_gcn_encoder(enc, x2, sg.view(k2), r0, r1, N, block, group)
+        views.insert(0, (x0, sg.view(None)))       # the reference's unused un-augmented view comes first (dropout draw order)
+    # The encoder passes of the views are independent: each runs on its own stream, so one view's all-gathers (NCCL stream)
+    # overlap another view's GEMMs / aggregation instead of idling the SMs; autograd replays each node on its forward stream,
+    # which overlaps the backward the same way.  The dropout draws are taken up front, in the reference's order.
+    main = torch.cuda.current_stream() if x.is_cuda else None
+    outs = []
+    if main is not None and OVERLAP_VIEWS:
+        streams = _view_streams(x.device, len(views))
+        for (xv, view), st in zip(views, streams):
+            st.wait_stream(main)
+            xv.record_stream(st)
+            with torch.cuda.stream(st):
+                outs.append(sharded_gcn_encoder(enc, xv, view, r0, r1, N, block, group))
+        for z, st in zip(outs, streams):
+            main.wait_stream(st)
+            z.record_stream(main)
+    else:
+        outs = [sharded_gcn_encoder(enc, xv, view, r0, r1, N, block, group) for xv, view in views]
+    z1, z2 = outs[-2], outs[-1]
     tau = module.contrast_model.loss.tau if hasattr(module.contrast_model, "loss") else 0.2
     return sharded_infonce_local(model.project(z1), model.project(z2), N, tau, group)
+
+
+#: run the views' encoder passes on separate CUDA streams (overlaps their NCCL all-gathers with compute)
+OVERLAP_VIEWS = True
+_VIEW_STREAMS: dict = {}
+
+
+def _view_streams(device, n):
+    key = (torch.device(device).index, n)
+    if key not in _VIEW_STREAMS:
+        _VIEW_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _VIEW_STREAMS[key]
 
 
 def allreduce_grads(params, group=None):
