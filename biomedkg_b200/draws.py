@@ -80,13 +80,39 @@ class DeviceDraws:
 
 
 class GraphSafeDraws(DeviceDraws):
-    """Draws for a CUDA-graph-captured step (biomedkg_b200/graphed.py).  A captured kernel's scalar arguments are frozen,
-    so the per-call dropout seed of ``DeviceDraws`` would replay the same mask forever; here the encoder dropout mask is
-    drawn by torch's device generator (whose Philox offset a captured graph advances on every replay) and handed to the
-    aggregation epilogue as an explicit keep mask."""
+    """Draws for a CUDA-graph-captured step (biomedkg_b200/graphed.py).
+
+    * A captured kernel's scalar arguments are frozen, so the per-call dropout seed of ``DeviceDraws`` would replay the same
+      mask forever: the encoder dropout mask is drawn by torch's device generator (whose Philox offset a captured graph
+      advances on every replay) and handed to the aggregation epilogue as an explicit keep mask.
+    * ``randperm`` (DGI / GGD corruption, model/gcl.py:17,66) comes from the CPU generator in the reference.  Here it returns a
+      STATIC device buffer; ``refresh()`` - called by ``GraphedStep`` before every replay - draws the permutation on the host
+      exactly as the reference does (``torch.randperm(n)``) and copies it into the buffer from pinned memory.
+    * ``coin`` (GGD's augmentation branch, model/gcl.py:74) is a host decision: one graph is captured per branch with the coin
+      pinned to that side (``coin_value``) and the host flips the real coin to choose which graph to replay."""
+
+    def __init__(self, coin_value=None):
+        super().__init__()
+        self._coin = coin_value
+        self._perms = {}
 
     def dropout(self, shape, p, device):
         return 0, torch.rand(shape, device=device) >= p
+
+    def randperm(self, n):
+        ent = self._perms.get(n)
+        if ent is None:
+            host = torch.randperm(n).pin_memory()
+            ent = self._perms[n] = (host.cuda(non_blocking=True), host)
+        return ent[0]
+
+    def refresh(self):
+        for n, (dev, host) in self._perms.items():
+            host.copy_(torch.randperm(n))
+            dev.copy_(host, non_blocking=True)
+
+    def coin(self):
+        return super().coin() if self._coin is None else self._coin
 
 
 class ReplayDraws:

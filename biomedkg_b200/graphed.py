@@ -11,7 +11,11 @@ workspaces and no host synchronisation; the random draws come from torch's devic
 captured graph advances per replay (``GraphSafeDraws`` replaces the host-seeded dropout stream by explicit masks).
 ``resort=True`` also captures the radix sort of ``edge_index`` - use it when every step brings a new edge list
 (mini-batches); with ``resort=False`` the sort is done once at capture time and only the features may change.
-Shapes are static: a new (N, E) needs a new ``GraphedStep``.  GRACE only (DGI / GGD draw from the CPU generator).
+Shapes are static: a new (N, E) needs a new ``GraphedStep``.
+
+DGI and GGD draw from the CPU generator inside the step (the corruption permutation, model/gcl.py:17,66, and GGD's
+augmentation coin, :74).  ``GraphSafeDraws`` turns the permutation into a static device buffer that the host refreshes
+before every replay, and ``graphed_step`` captures GGD once per coin branch and lets the host's coin pick the graph.
 """
 from __future__ import annotations
 
@@ -25,13 +29,11 @@ from .draws import GraphSafeDraws, set_draws
 
 class GraphedStep:
     def __init__(self, module, x: torch.Tensor, edge_index: torch.Tensor, resort: bool = False, warmup: int = 3,
-                 loss_fn=None):
-        from .model.gcl import GRACE
+                 loss_fn=None, coin_value=None):
+        from .model.gcl import GGD
 
-        if loss_fn is None and not isinstance(getattr(module, "model", None), GRACE):
-            # DGI's permutation and GGD's coin come from the CPU generator (model/gcl.py:17,66): a captured graph would
-            # replay the one permutation / branch it saw at capture time
-            raise NotImplementedError("GraphedStep captures the GRACE step; DGI / GGD draw from the CPU generator inside the step")
+        if loss_fn is None and isinstance(getattr(module, "model", None), GGD) and coin_value is None:
+            raise ValueError("GGD's augmentation coin is a host-side branch: capture one graph per branch (graphed_step(module, ...))")
         ops._need_cuda(x, edge_index)
         self.module = module
         self.resort = bool(resort)
@@ -39,7 +41,8 @@ class GraphedStep:
         self.edge_index = edge_index.clone()
         self._batch = SimpleNamespace(x=self.x, edge_index=self.edge_index)
         self._loss_fn = loss_fn or (lambda m, b: m.training_step(b))
-        set_draws(module, GraphSafeDraws())
+        self.draws = GraphSafeDraws(coin_value)
+        set_draws(module, self.draws)
         params = [p for p in module.parameters() if p.requires_grad]
         side = torch.cuda.Stream(device=x.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -89,6 +92,8 @@ class GraphedStep:
         for p, g in zip(self.params, self.grads):
             if p.grad is not g:
                 p.grad = g
+        set_draws(self.module, self.draws)     # another captured branch of the same module may have installed its own
+        self.draws.refresh()                   # host-side draws of this step (corruption permutations) into the static buffers
         self.graph.replay()
         return self.loss
 
@@ -97,3 +102,29 @@ def _launch_counter() -> int:
     from . import _cabi
 
     return _cabi.kernel_launches
+
+
+class GraphedGGDStep:
+    """GGD (model/gcl.py:54-93): the coin ``torch.rand(1) < p`` decides on the host whether the positive pass is augmented, so
+    the step is captured twice - coin pinned below / above ``p`` - and every call flips the real coin (CPU generator, the
+    reference's draw) and replays the matching graph."""
+
+    def __init__(self, module, x, edge_index, **kw):
+        self.module = module
+        self.p = float(module.model.p)
+        self.branches = {True: GraphedStep(module, x, edge_index, coin_value=0.0, **kw),
+                         False: GraphedStep(module, x, edge_index, coin_value=1.0, **kw)}
+        self.launches_per_replay = max(b.launches_per_replay for b in self.branches.values())
+
+    def __call__(self, x=None, edge_index=None):
+        aug = float(torch.rand(1).item()) < self.p
+        return self.branches[aug](x, edge_index)
+
+
+def graphed_step(module, x, edge_index, **kw):
+    """The captured training step for any of the three GCL modules."""
+    from .model.gcl import GGD
+
+    if isinstance(getattr(module, "model", None), GGD):
+        return GraphedGGDStep(module, x, edge_index, **kw)
+    return GraphedStep(module, x, edge_index, **kw)

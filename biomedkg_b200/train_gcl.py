@@ -2,9 +2,11 @@
 
     python -m biomedkg_b200.train_gcl --model grace --nodes 8000 --edges 200000 --epochs 5
 
-Full-graph training on a synthetic graph of the requested shape: seed_everything(42) (configs/gcl.yaml:6), Adam over
-``module.model`` only, cosine/linear warm-up schedule sized in steps, gradient clip 1.0 (train_gcl.py:99), JSONL log of
-loss and nodes/s (the reference logs to Comet)."""
+``--regime fullgraph`` (default): full-graph training on a synthetic graph of the requested shape.  ``--regime minibatch``: the
+reference's own loop - RandomLinkSplit(0.1, 0.2) -> NeighborLoader([30]*3, batch 64, shuffle) -> fit (train + validation every
+epoch) -> test (train_gcl.py:108-122, data_module.py:65-99), with the GPU sampler of loader.py.  Both: seed_everything(42)
+(configs/gcl.yaml:6), Adam over ``module.model`` only, cosine/linear warm-up schedule sized in steps, gradient clip 1.0
+(train_gcl.py:99), JSONL log of the losses and nodes/s (the reference logs to Comet)."""
 from __future__ import annotations
 
 import argparse
@@ -12,6 +14,61 @@ import json
 import time
 
 import torch
+
+
+def _evaluate(mod, loader, step_name):
+    """validation / test epoch of the Lightning loop: module.validation_step / test_step over a loader, no gradients."""
+    total, n = 0.0, 0
+    mod.eval()
+    with torch.no_grad():
+        for i, batch in enumerate(loader):
+            total += float(getattr(mod, step_name)(batch, i))
+            n += 1
+    mod.train()
+    return total / max(n, 1)
+
+
+def run_minibatch(a, mod, data, opt, log):
+    """The reference's own regime (train_gcl.py:108-122 over GCLDataModule, data_module.py:65-99): RandomLinkSplit(0.1, 0.2) ->
+    NeighborLoader([30]*3, batch_size, shuffle=True) for training, the same loader over the validation / test splits,
+    ``trainer.fit`` (train + validate every epoch) then ``trainer.test``."""
+    from .loader import NeighborLoader, random_link_split
+
+    train_d, val_d, test_d = random_link_split(data, num_val=0.1, num_test=0.2)
+    fan = [a.fanout] * a.hops
+    train_l = NeighborLoader(train_d, fan, batch_size=a.batch_size, shuffle=True)
+    val_l = NeighborLoader(val_d, fan, batch_size=a.val_batch_size, shuffle=False)
+    test_l = NeighborLoader(test_d, fan, batch_size=a.val_batch_size, shuffle=False)
+    steps = a.epochs * (min(len(train_l), a.limit_batches) if a.limit_batches else len(train_l))
+    sched = mod._get_scheduler(opt, num_training_steps=steps)
+    for epoch in range(a.epochs):
+        torch.cuda.synchronize()
+        t0, seen, tot, nb = time.perf_counter(), 0, 0.0, 0
+        for i, batch in enumerate(train_l):
+            if a.limit_batches and i >= a.limit_batches:
+                break
+            opt.zero_grad(set_to_none=True)
+            loss = mod.training_step(batch, i)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(mod.model.parameters(), 1.0)
+            opt.step()
+            sched.step()
+            tot += float(loss.detach())
+            nb += 1
+            seen += int(batch.x.size(0))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        val = _evaluate(mod, _limited(val_l, a.limit_batches), "validation_step")
+        log({"epoch": epoch, "train_loss": tot / max(nb, 1), "val_loss": val, "batches": nb, "sampled_nodes_per_s": seen / dt,
+             "lr": sched.get_last_lr()[0]})
+    log({"test_loss": _evaluate(mod, _limited(test_l, a.limit_batches), "test_step")})
+
+
+def _limited(loader, k):
+    for i, b in enumerate(loader):
+        if k and i >= k:
+            return
+        yield b
 
 
 def main():
@@ -34,7 +91,14 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--log", default=None)
     ap.add_argument("--cuda-graph", action="store_true",
-                    help="replay forward+backward from a CUDA graph (graphed.GraphedStep; GRACE only, fixed full graph)")
+                    help="replay forward+backward from a CUDA graph (graphed.graphed_step; fixed full graph)")
+    ap.add_argument("--regime", default="fullgraph", choices=["fullgraph", "minibatch"],
+                    help="fullgraph: one full-graph step per epoch; minibatch: the reference's RandomLinkSplit + NeighborLoader loop with validation and test")
+    ap.add_argument("--batch-size", type=int, default=64)
+    ap.add_argument("--val-batch-size", type=int, default=128)
+    ap.add_argument("--fanout", type=int, default=30)
+    ap.add_argument("--hops", type=int, default=3)
+    ap.add_argument("--limit-batches", type=int, default=0, help="cap the batches per epoch / evaluation (0 = all)")
     a = ap.parse_args()
 
     torch.manual_seed(a.seed)
@@ -56,15 +120,22 @@ def main():
     Batch.x = x.to(dev)
     Batch.edge_index = torch.randint(0, a.nodes, (2, a.edges), generator=g, dtype=torch.int64).to(dev)
     opt = torch.optim.Adam(mod.model.parameters(), lr=a.learning_rate)
-    sched = mod._get_scheduler(opt, num_training_steps=a.epochs)
     out = open(a.log, "a") if a.log else None
+
+    def log(rec):
+        print(json.dumps(rec))
+        if out:
+            out.write(json.dumps(rec) + "\n")
+
+    if a.regime == "minibatch":
+        run_minibatch(a, mod, Batch, opt, log)
+        return
+    sched = mod._get_scheduler(opt, num_training_steps=a.epochs)
     graphed = None
     if a.cuda_graph:
-        if a.model != "grace":
-            raise SystemExit("--cuda-graph: DGI / GGD draw from the CPU generator inside the step; only GRACE is capturable")
-        from .graphed import GraphedStep
+        from .graphed import graphed_step
 
-        graphed = GraphedStep(mod, Batch.x, Batch.edge_index, resort=False)
+        graphed = graphed_step(mod, Batch.x, Batch.edge_index, resort=False)
     for epoch in range(a.epochs):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -79,10 +150,7 @@ def main():
         sched.step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        rec = {"epoch": epoch, "train_loss": float(loss.detach()), "nodes_per_s": a.nodes / dt, "lr": sched.get_last_lr()[0]}
-        print(json.dumps(rec))
-        if out:
-            out.write(json.dumps(rec) + "\n")
+        log({"epoch": epoch, "train_loss": float(loss.detach()), "nodes_per_s": a.nodes / dt, "lr": sched.get_last_lr()[0]})
 
 
 if __name__ == "__main__":

@@ -86,3 +86,50 @@ def sample(edge_index: np.ndarray, num_nodes: int, seeds, num_neighbors, seed: i
         begin, end = end, len(nodes)
     return (np.asarray(nodes, dtype=np.int64), np.asarray([rows, cols], dtype=np.int64).reshape(2, -1),
             np.asarray(eids, dtype=np.int64))
+
+
+def check_structure(edge_index: np.ndarray, num_nodes: int, seeds, num_neighbors, n_id, sub, e_id):
+    """Brute-force check of a sampled batch against PyG NeighborLoader's published STRUCTURAL rules, independent of any random
+    stream (it never calls ``draw`` / ``pick_positions``): returns a list of violated rules (empty = the batch is valid).
+
+      1. the seeds come first in ``n_id``, which has no duplicates;
+      2. every sampled edge IS an original edge: (n_id[row], n_id[col]) == edge_index[:, e_id];
+      3. no replacement: e_id has no duplicates;
+      4. fan-out cap: a node expanded in a hop with fan-out f contributes exactly min(in_degree, f) in-edges (all of them for
+         f = -1); a node is expanded in the hop after the one that added it, nodes added by the last hop are not expanded;
+      5. new nodes are appended in order of first appearance as a source within the hop that adds them;
+      6. edges are grouped by hop and, inside a hop, by target in frontier order."""
+    src, dst = edge_index[0].astype(np.int64), edge_index[1].astype(np.int64)
+    n_id, sub, e_id = np.asarray(n_id), np.asarray(sub), np.asarray(e_id)
+    bad = []
+    S = len(seeds)
+    if list(n_id[:S]) != [int(s) for s in seeds] or len(set(n_id.tolist())) != len(n_id):
+        bad.append("1 seeds-first / distinct nodes")
+    if sub.shape[1] != len(e_id) or (len(e_id) and (not np.array_equal(n_id[sub[0]], src[e_id]) or not np.array_equal(n_id[sub[1]], dst[e_id]))):
+        bad.append("2 sampled edges are original edges")
+    if len(set(e_id.tolist())) != len(e_id):
+        bad.append("3 no replacement")
+    indeg = np.bincount(dst, minlength=num_nodes)
+    begin, end, pos, known = 0, S, 0, S
+    for hop, f in enumerate(num_neighbors):
+        hop_begin = pos
+        for t in range(begin, end):                                  # frontier of this hop, in order
+            want = int(indeg[n_id[t]]) if (f < 0 or indeg[n_id[t]] < f) else f
+            got = 0
+            while pos < sub.shape[1] and sub[1, pos] == t:
+                got += 1
+                pos += 1
+            if got != want:
+                bad.append(f"4/6 hop {hop} target {t}: {got} edges, expected {want}")
+                return bad
+        first_seen = []
+        for r in sub[0, hop_begin:pos].tolist():
+            if r >= known and r not in first_seen:
+                first_seen.append(r)
+        if first_seen != list(range(known, known + len(first_seen))):
+            bad.append(f"5 first-appearance order in hop {hop}")
+        begin, end = end, known + len(first_seen)
+        known = end
+    if pos != sub.shape[1] or known != len(n_id):
+        bad.append("6 trailing edges / nodes not accounted for")
+    return bad

@@ -51,6 +51,22 @@ def test_sampler_bit_exact_vs_oracle(n, e, fan, nseeds, hub):
     assert torch.equal(first_hop_a[: first_hop_b.numel()], first_hop_b[: first_hop_a.numel()])
 
 
+@pytest.mark.parametrize("n,e,fan,nseeds", [(400, 30000, [30, 30, 30], 64), (5000, 40000, [30, 30, 30], 128), (300, 9000, [-1], 1), (1000, 50000, [7, 3], 20)])
+def test_sampler_structure_brute_force(n, e, fan, nseeds):
+    """PyG NeighborLoader's structural rules (fan-out cap, no replacement, sampled edges are original edges, seeds first,
+    first-appearance node order, hop/target grouping) checked by brute force on the GPU sampler's output - the checker
+    (oracle.sampler.check_structure) shares no random stream or code with the kernels."""
+    from biomedkg_b200.loader import NeighborSampler
+    from oracle import sampler as osamp
+
+    ei = _graph(n, e, 7 * n + e)
+    seeds = torch.randperm(n, generator=torch.Generator().manual_seed(n))[:nseeds]
+    smp = NeighborSampler(ei.to(DEV), n, fan)
+    for seed in (1, 99, 2 ** 40 + 17):
+        n_id, sub, eid = smp.sample(seeds.to(DEV), seed)
+        assert osamp.check_structure(ei.numpy(), n, seeds.tolist(), fan, n_id.cpu().numpy(), sub.cpu().numpy(), eid.cpu().numpy()) == []
+
+
 def test_loader_contract_and_training_step():
     import biomedkg_b200 as b
     from biomedkg_b200.loader import NeighborLoader, random_link_split
@@ -108,3 +124,22 @@ def test_one_hop_loader_reproduces_the_export_path():
             rows.append(mod(batch.x, batch.edge_index)[: batch.batch_size])
     got = torch.cat(rows)
     assert got.shape == ref.shape and rel_err(got, ref) < 5e-3
+
+
+def test_train_driver_minibatch_regime_runs_fit_validate_test():
+    """biomedkg_b200.train_gcl --regime minibatch = the reference's train_gcl.py:108-122 loop (RandomLinkSplit -> NeighborLoader ->
+    fit with validation every epoch -> test) on the GPU sampler: JSONL records carry train / val / test losses."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "biomedkg_b200.train_gcl", "--regime", "minibatch", "--model", "grace", "--nodes", "3000",
+                        "--edges", "40000", "--in-dim", "64", "--hidden-dim", "64", "--epochs", "2", "--limit-batches", "4",
+                        "--batch-size", "64"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    recs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    epochs = [x for x in recs if "epoch" in x]
+    assert len(epochs) == 2 and all(x["batches"] == 4 and x["train_loss"] == x["train_loss"] and x["val_loss"] == x["val_loss"] for x in epochs)
+    assert "test_loss" in recs[-1] and recs[-1]["test_loss"] == recs[-1]["test_loss"]

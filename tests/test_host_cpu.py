@@ -86,3 +86,26 @@ def test_graphed_step_refuses_objectives_with_host_side_draws():
     with pytest.raises(RuntimeError):      # GRACE passes the objective check and then fails loudly on CPU tensors (no CPU path)
         GraphedStep(b.GRACEModule(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2), torch.zeros(8, 32),
                     torch.zeros(2, 4, dtype=torch.int64))
+
+
+def test_sampler_structure_checker_accepts_oracle_and_rejects_corruptions():
+    """oracle.sampler.check_structure is the stream-independent judge of a sampled batch (used on the GPU sampler's output in
+    tests/test_gpu_sampler.py): it must accept the oracle's own batches and flag each kind of corruption."""
+    import numpy as np
+
+    from oracle import sampler as osamp
+
+    rng = np.random.default_rng(0)
+    n, e = 120, 3000
+    ei = rng.integers(0, n - 5, size=(2, e))
+    seeds = [3, 77, 10, 54]
+    for fan in ([5, 5], [30, 30, 30], [-1], [-1, 2]):
+        n_id, sub, eid = osamp.sample(ei, n, seeds, fan, 1234)
+        assert osamp.check_structure(ei, n, seeds, fan, n_id, sub, eid) == []
+        if sub.shape[1] > 4:
+            dup = eid.copy(); dup[1] = dup[0]
+            sub2 = sub.copy(); sub2[:, 1] = sub2[:, 0]
+            assert osamp.check_structure(ei, n, seeds, fan, n_id, sub2, dup)                  # replacement
+            assert osamp.check_structure(ei, n, seeds, fan, n_id, sub[:, :-1], eid[:-1])      # a missing edge breaks the fan-out count
+            sw = n_id.copy(); sw[[len(seeds), len(n_id) - 1]] = sw[[len(n_id) - 1, len(seeds)]]
+            assert osamp.check_structure(ei, n, seeds, fan, sw, sub, eid)                      # wrong node order
