@@ -351,7 +351,23 @@ def run_ours(args, rank, world, local_rank):
     # CUDA-graph replay pays off when the step is launch-bound (cfg1 / cfg2: a few ms of 5-50 us kernels).  At cfg4 / cfg5 the step
     # is ~100 ms of long kernels, and a captured graph would pin the InfoNCE E store (up to 135 GB) in a private memory pool per
     # capture - so those run eagerly, where torch's caching allocator hands the same block back every step.
-    use_graph = args.graph == "on" or (args.graph == "auto" and not rowshard and N <= 50_000)
+    # Row-sharded steps are short again (cfg4 on 8 GPUs: ~19 ms for ~350 launches per rank, 8 Python processes on the host's
+    # cores): issued eagerly the ranks drift apart and wait for each other inside the all-gathers, so the step - NCCL collectives
+    # included - is captured and replayed as well.
+    use_graph = args.graph == "on" or (args.graph == "auto" and (N <= 50_000 or rowshard))
+    shard_loss = None
+    if full_shard:
+        from biomedkg_b200.dist import sharded_grace_loss as _sgl
+
+        shard_loss = lambda m, bt: _sgl(m, bt.x, bt.edge_index, num_nodes=N)  # noqa: E731
+
+    def all_ranks_ok(ok):
+        """a capture that failed on ANY rank must send every rank back to eager launches (mismatched collectives would hang)"""
+        if world == 1:
+            return ok
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
     graphed = {}      # "resident" / "e2e" -> GraphedStep (captured lazily, after the eager warm-up)
 
     def tail():
@@ -370,6 +386,10 @@ def run_ours(args, rank, world, local_rank):
         """forward + backward replayed from a CUDA graph (biomedkg_b200/graphed.py); all-reduce / clip / Adam eager."""
         gs = graphed[kind]
         loss = gs(batch.x, batch.edge_index) if kind == "e2e" else gs()
+        if full_shard:
+            from biomedkg_b200.dist import allreduce_grads
+
+            allreduce_grads(params)
         tail()
         return loss
 
@@ -397,7 +417,14 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and not args.no_clocks:
         sampler.start()                      # started before warm-up so it is already streaming in the timed region
     res = Batch()
-    res.x, res.edge_index = x_host.to(dev), ei_host.to(dev)
+    if full_shard:   # every rank holds only its node block of the features (the whole edge_index stays replicated)
+        from biomedkg_b200.dist import shard_layout as _sl
+
+        _b0, _b1 = _sl(N, world)[1][rank]
+        res.x, res.num_nodes = x_host[_b0:_b1].to(dev), N
+    else:
+        res.x = x_host.to(dev)
+    res.edge_index = ei_host.to(dev)
     for _ in range(args.warmup):
         step(res)
     barrier()
@@ -406,12 +433,16 @@ def run_ours(args, rank, world, local_rank):
         from biomedkg_b200.graphed import GraphedStep
 
         opt.zero_grad(set_to_none=True)
+        ok = True
         try:
-            graphed["resident"] = GraphedStep(mod, res.x, res.edge_index, resort=False)   # edge list fixed: sorted once, as in the eager loop
+            graphed["resident"] = GraphedStep(mod, res.x, res.edge_index, resort=False, loss_fn=shard_loss)   # edge list fixed: sorted once, as in the eager loop
         except Exception as exc:  # noqa: BLE001 - a failed capture must not cost the measurement: fall back to eager launches
             print(f"[bench] CUDA-graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
-            use_graph = False
+            ok = False
             torch.cuda.synchronize()
+        if not all_ranks_ok(ok):
+            use_graph = False
+            graphed.pop("resident", None)
     timed = {"bmkg_infonce_fwd", "bmkg_infonce_bwd", "bmkg_infonce_fwd_rows", "bmkg_infonce_bwd_rows", "bmkg_gcn_aggregate_rows",
              "bmkg_gat_aggregate", "bmkg_gat_aggregate_bwd"}
     if use_graph:
@@ -492,12 +523,16 @@ def run_ours(args, rank, world, local_rank):
     if e2e_graph:
         graphed.pop("resident", None)          # release its memory pool before the second capture
         opt.zero_grad(set_to_none=True)
+        ok = True
         try:
-            graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True)    # every step brings its own edge_index: sort captured too
+            graphed["e2e"] = GraphedStep(mod, res.x, res.edge_index, resort=True, loss_fn=shard_loss)    # every step brings its own edge_index: sort captured too
         except Exception as exc:  # noqa: BLE001
             print(f"[bench] CUDA-graph capture of the end-to-end step failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
-            e2e_graph = False
+            ok = False
             torch.cuda.synchronize()
+        if not all_ranks_ok(ok):
+            e2e_graph = False
+            graphed.pop("e2e", None)
     run_e2e = (lambda bt: graph_step("e2e", bt)) if e2e_graph else step
 
     def e2e_loop(k):
