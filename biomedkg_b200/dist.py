@@ -84,7 +84,7 @@ class CudaImpl:
         if r1 > r0:
             from .ops import alloc_e_store
 
-            W = torch.exp2(A)                                # padding entries: a = 0 -> w = 1
+            W = torch.exp(A * 0.6931471805599453)            # 2^a (not torch.exp2: a jiterator kernel, NVRTC-compiled at run time); padding: a = 0 -> w = 1
             ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
             self.e_store = alloc_e_store(N, B, r0, r1, Z.device)      # E = 2^S of this rank's rows, kept for the backward if it fits
             call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(W), N, B, D, r0, r1, _p(loss), _p(qw), _p(self.e_store), _p(ws), ws.numel(),
