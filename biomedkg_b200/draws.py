@@ -58,8 +58,24 @@ def hash_keep_mask16(seed: int, numel: int, p: float) -> torch.Tensor:
 
 
 class DeviceDraws:
-    def __init__(self):
+    """``stream`` separates the counter-hash dropout streams of different owners (encoder, ReDAF, ...: every instance gets its
+    own id), ``salt`` lets data-parallel ranks that each train on their OWN graph decorrelate their masks (set it to the
+    rank; the row-sharded path must keep it equal on all ranks - they evaluate one global mask), and ``counter`` can be
+    restored from a checkpoint (``state`` / ``load_state``) so a resumed run does not replay the masks it already used."""
+
+    _instances = 0
+
+    def __init__(self, salt: int = 0):
         self._counter = 0
+        DeviceDraws._instances += 1
+        self.stream = DeviceDraws._instances
+        self.salt = int(salt)
+
+    def state(self):
+        return {"counter": self._counter, "stream": self.stream, "salt": self.salt}
+
+    def load_state(self, st):
+        self._counter, self.stream, self.salt = int(st["counter"]), int(st["stream"]), int(st["salt"])
 
     def feature_mask(self, x, p):
         return torch.rand_like(x, dtype=torch.float32) >= p
@@ -70,7 +86,7 @@ class DeviceDraws:
     def dropout(self, shape, p, device):
         """-> (seed, explicit_keep_mask_or_None) for the fused aggregation epilogue."""
         self._counter += 1
-        return _splitmix(torch.initial_seed() ^ _splitmix(self._counter)), None
+        return _splitmix(torch.initial_seed() ^ _splitmix(self._counter) ^ _splitmix((self.stream << 32) ^ self.salt ^ 0x5bd1e995)), None
 
     def randperm(self, n):
         return torch.randperm(n)

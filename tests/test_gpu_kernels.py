@@ -343,3 +343,27 @@ def test_redaf_training_reference_golden(golden_dir):
             assert rel_err(p.grad, fx["grads"][k]) < 6e-2, k
         else:
             assert p.grad is None, k
+
+
+def test_relu_with_fp32_output_is_rejected_and_conv_default_is_safe():
+    """the fused ReLU/dropout backward re-reads the saved OUTPUT as bf16, so relu=True with an fp32 output would
+    reinterpret fp32 bits.  The op refuses the combination; the conv layers' default (out_fp32=None) picks bf16 when ReLU is
+    fused and fp32 otherwise, and the gradient of the public call matches the unfused composition."""
+    import biomedkg_b200 as b
+    from biomedkg_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    n, e = 300, 3000
+    x = torch.randn(n, 64, generator=g).to(DEV)
+    ei = torch.randint(0, n, (2, e), generator=g).to(DEV)
+    for conv in (b.model.encoder.GCNConv(64, 64).to(DEV), b.model.encoder.GATConv(64, 64).to(DEV)):
+        with pytest.raises(ValueError):
+            conv(x, ei, relu=True, out_fp32=True)
+        y = conv(x, ei, relu=True)
+        assert y.dtype == torch.bfloat16 and conv(x, ei).dtype == torch.float32
+        y.float().square().sum().backward()
+        g_fused = conv.lin.weight.grad.clone()
+        conv.lin.weight.grad = None
+        y2 = torch.relu(conv(x, ei))
+        y2.square().sum().backward()
+        assert rel_err(g_fused, conv.lin.weight.grad) < 2e-2
