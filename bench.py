@@ -218,7 +218,7 @@ def _make_module(cfg, dev):
                          fuse_method=cfg["fuse"], encoder=cfg["encoder"]).to(dev).train()
 
 
-def side_workload(name, dev, steps, warmup, use_graph=True):
+def side_workload(name, dev, steps, warmup, use_graph=True, peak_tf=None):
     """Device-resident nodes/s of another BASELINE configuration on this GPU (N=1 'also' entries): same step, same timing rules."""
     from biomedkg_b200.graphed import GraphedStep
 
@@ -268,6 +268,21 @@ def side_workload(name, dev, steps, warmup, use_graph=True):
     ms = e0.elapsed_time(e1) / steps
     out = {"value": cfg["N"] / (ms * 1e-3), "unit": "nodes/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "nodes": cfg["N"],
            "edges": cfg["E"], "cuda_graph": graphed, "final_loss": float(loss.detach()), "workload": f"{name}: {cfg['desc']}"}
+    # InfoNCE kernels at this size, timed with CUDA events in three eager steps (events cannot bracket kernels inside a replay)
+    from biomedkg_b200 import _cabi
+
+    _cabi.timed_entries.update({"bmkg_infonce_fwd", "bmkg_infonce_bwd"})
+    _cabi.timings.clear()
+    for _ in range(3):
+        eager()
+    torch.cuda.synchronize()
+    km = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _cabi.timings.items()}
+    _cabi.timed_entries.clear()
+    _cabi.timings.clear()
+    if "bmkg_infonce_bwd" in km and peak_tf:
+        n2d = float(cfg["N"]) ** 2 * HID
+        out["infonce"] = {"bwd_ms": km["bmkg_infonce_bwd"], "bwd_frac_of_sustained_bf16_peak (8N^2D credited)": 8.0 * n2d / (km["bmkg_infonce_bwd"] * 1e-3) / 1e12 / peak_tf,
+                          "fwd_ms": km.get("bmkg_infonce_fwd"), "fwd_frac (6N^2D credited)": 6.0 * n2d / (km["bmkg_infonce_fwd"] * 1e-3) / 1e12 / peak_tf}
     del mod, opt, bt
     torch.cuda.empty_cache()
     return out
@@ -631,7 +646,7 @@ def run_ours(args, rank, world, local_rank):
         for name in ("cfg2", "cfg1"):
             if name != args.config:
                 try:
-                    also[name] = side_workload(name, dev, max(3, min(args.steps, 20)), 3)
+                    also[name] = side_workload(name, dev, max(3, min(args.steps, 20)), 3, peak_tf=peak_tf)
                 except Exception as exc:  # noqa: BLE001
                     also[name] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         try:
