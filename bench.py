@@ -183,7 +183,7 @@ def run_reference(args, rank, world):
         also["cfg1_full"] = {"value": r1, "unit": "nodes/s", "s_per_step": d1, "steps": 3, "warmup": 1, "nodes": CONFIGS["cfg1"]["N"],
                              "edges": CONFIGS["cfg1"]["E"], "same_config_as": "also.cfg1 of the GPU arm"}
         avail = _mem_available_gb()
-        if avail >= 100.0 and time.time() - t0 < 120:
+        if avail >= 200.0 and time.time() - t0 < 120:   # the as-written step peaks near 100 GB at 28k nodes: leave a wide margin, an OOM-killed box helps nobody
             try:
                 r2, d2, _ = cpu_reference_step_rate(CONFIGS["cfg2"], CONFIGS["cfg2"]["N"], 1, 0)
                 also["cfg2_full"] = {"value": r2, "unit": "nodes/s", "s_per_step": d2, "steps": 1, "warmup": 0, "nodes": CONFIGS["cfg2"]["N"],
@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
             except (RuntimeError, MemoryError) as exc:
                 also["cfg2_full"] = {"unavailable": f"reference OOM ({type(exc).__name__})"}
         else:
-            also["cfg2_full"] = {"unavailable": f"reference OOM: the as-written loss needs ~45-90 GB, MemAvailable = {avail:.0f} GB"}
+            also["cfg2_full"] = {"unavailable": f"reference OOM: the as-written loss needs ~100 GB at 28k nodes, MemAvailable = {avail:.0f} GB (run only with >= 200 GB)"}
     line = {
         "impl": "reference", "metric": "GCL nodes/sec", "value": rate, "unit": "nodes/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if args.mode == "rowshard" else "weak",

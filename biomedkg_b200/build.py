@@ -52,9 +52,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
 
+    extra = os.environ.get("BMKG_NVCC_DEFS", "").split()      # e.g. "-DBMKG_POLY_FWD=0 -DBMKG_POLY_BWD=0" for A/B tuning builds
+
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -66,10 +68,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"], capture_output=True, text=True)
+    out = os.environ.get("BMKG_LIB_OUT", LIB)
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

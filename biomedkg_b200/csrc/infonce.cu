@@ -64,6 +64,33 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x for two values on the FMA pipe (packed fp32x2): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 minimax
+// polynomial for 2^f (max relative error 2.7e-6, mean 4e-8), exponent added through the integer view.  Valid for |x| < 120.
+// Evaluated in round 2 as a way to take exponentials off the MUFU pipe (ncu: forward tensor 72.7 % = XU 72.7 %) and found NOT
+// to pay on B200: with 1 of 4 (forward) / 1 of 2 (backward) pairs on the polynomial the forward is unchanged within noise
+// (1.31-1.42 ms at N = 28k, 7.0-7.8 ms at 65k) and the backward slows down (2.41 -> 2.54 ms; all-polynomial 2.80 ms) - the
+// extra FMA-pipe instructions cost more than the MUFU slots they free.  Kept behind compile-time switches, default off
+// (BMKG_NVCC_DEFS="-DBMKG_POLY_FWD=1 -DBMKG_POLY_BWD=1" python biomedkg_b200/build.py --force).
+#ifndef BMKG_POLY_FWD
+#define BMKG_POLY_FWD 0   // forward: pairs per group of 4 pairs evaluated by the polynomial (0 = all MUFU)
+#endif
+#ifndef BMKG_POLY_BWD
+#define BMKG_POLY_BWD 0   // backward: pairs per group of 2 pairs
+#endif
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));           // 1.5 * 2^23: the integer part lands in the mantissa
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(f, make_float2(0.009570101276040077f, 0.009570101276040077f), make_float2(0.05591785907745361f, 0.05591785907745361f));
+  p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+  p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+  p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)), __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+__device__ __forceinline__ float2 ex2_pair(uint32_t a, uint32_t b, bool poly) {
+  return poly ? ex2_poly2(make_float2(__uint_as_float(a), __uint_as_float(b))) : make_float2(ex2(__uint_as_float(a)), ex2(__uint_as_float(b)));
+}
+
 struct Schedule {
   int rb0, nrb, ntiles, nchunks, tiles_per_chunk;  // row blocks [rb0, rb0 + nrb) of this launch (row-sharded multi-GPU)
 };
@@ -229,17 +256,17 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           if (diag) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j == lrow) r[j] = 0xff800000u;  // -inf -> ex2 = 0
+              if (c * 32 + j == lrow) r[j] = 0xc2c80000u;  // -100.0f -> 2^-100: nothing next to the other terms (finite, so both ex2 paths take it)
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             // 2^(S + a_v) = 2^S w_v: the column factor rides on the accumulate (one packed FFMA per two elements) and the
             // load is off the ex2 dependency chain
             const float4 wa = __ldg(wvp + c * 8 + (j >> 2)), wb = __ldg(wvp + c * 8 + (j >> 2) + 1);
-            const float2 e01 = make_float2(ex2(__uint_as_float(r[j])), ex2(__uint_as_float(r[j + 1])));
-            const float2 e23 = make_float2(ex2(__uint_as_float(r[j + 2])), ex2(__uint_as_float(r[j + 3])));
-            const float2 e45 = make_float2(ex2(__uint_as_float(r[j + 4])), ex2(__uint_as_float(r[j + 5])));
-            const float2 e67 = make_float2(ex2(__uint_as_float(r[j + 6])), ex2(__uint_as_float(r[j + 7])));
+            const float2 e01 = ex2_pair(r[j], r[j + 1], BMKG_POLY_FWD >= 3);
+            const float2 e23 = ex2_pair(r[j + 2], r[j + 3], BMKG_POLY_FWD >= 2);
+            const float2 e45 = ex2_pair(r[j + 4], r[j + 5], BMKG_POLY_FWD >= 4);
+            const float2 e67 = ex2_pair(r[j + 6], r[j + 7], BMKG_POLY_FWD >= 1);
             s01 = __ffma2_rn(e01, make_float2(wa.x, wa.y), s01);
             s23 = __ffma2_rn(e23, make_float2(wa.z, wa.w), s23);
             s01 = __ffma2_rn(e45, make_float2(wb.x, wb.y), s01);
@@ -529,8 +556,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
             // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
             const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
             const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
-            float2 p01 = __fmul2_rn(make_float2(ex2(__uint_as_float(r[4 * q + 0])), ex2(__uint_as_float(r[4 * q + 1]))), t01);
-            float2 p23 = __fmul2_rn(make_float2(ex2(__uint_as_float(r[4 * q + 2])), ex2(__uint_as_float(r[4 * q + 3]))), t23);
+            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), t01);
+            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), t23);
             if (diag) {
               const int j = gcol0 + c * 32 + 4 * q;
               if (j + 0 == row) p01.x = 0.f;
