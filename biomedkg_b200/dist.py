@@ -371,7 +371,9 @@ def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
 
 
 #: run the views' encoder passes on separate CUDA streams (overlaps their NCCL all-gathers with compute)
-OVERLAP_VIEWS = False      # measured on 4 x B200 (cfg4): 32.5 -> 32.4 ms, the all-gather kernels then compete with the compute for SMs
+import os as _os
+
+OVERLAP_VIEWS = _os.environ.get("BMKG_OVERLAP_VIEWS", "0") == "1"      # measured on 4 x B200 (cfg4): 32.5 -> 32.4 ms, the all-gather kernels then compete with the compute for SMs
 _VIEW_STREAMS: dict = {}
 
 
