@@ -348,40 +348,12 @@ def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
     views = [(x1, sg.view(k1)), (x2, sg.view(k2))]
     if not model.skip_unused_view:
         views.insert(0, (x0, sg.view(None)))       # the reference's unused un-augmented view comes first (dropout draw order)
-    # The encoder passes of the views are independent: each runs on its own stream, so one view's all-gathers (NCCL stream)
-    # overlap another view's GEMMs / aggregation instead of idling the SMs; autograd replays each node on its forward stream,
-    # which overlaps the backward the same way.  The dropout draws are taken up front, in the reference's order.
-    main = torch.cuda.current_stream() if x.is_cuda else None
-    outs = []
-    if main is not None and OVERLAP_VIEWS:
-        streams = _view_streams(x.device, len(views))
-        for (xv, view), st in zip(views, streams):
-            st.wait_stream(main)
-            xv.record_stream(st)
-            with torch.cuda.stream(st):
-                outs.append(sharded_gcn_encoder(enc, xv, view, r0, r1, N, block, group))
-        for z, st in zip(outs, streams):
-            main.wait_stream(st)
-            z.record_stream(main)
-    else:
-        outs = [sharded_gcn_encoder(enc, xv, view, r0, r1, N, block, group) for xv, view in views]
+    # (Tried in round 2: one CUDA stream per view so that a view's all-gathers overlap another view's compute - 32.5 -> 32.4 ms
+    # at 4 GPUs, 19.6 -> 19.0 ms at 8, not worth the cross-stream allocator hazards; the passes run back to back.)
+    outs = [sharded_gcn_encoder(enc, xv, view, r0, r1, N, block, group) for xv, view in views]
     z1, z2 = outs[-2], outs[-1]
     tau = module.contrast_model.loss.tau if hasattr(module.contrast_model, "loss") else 0.2
     return sharded_infonce_local(model.project(z1), model.project(z2), N, tau, group)
-
-
-#: run the views' encoder passes on separate CUDA streams (overlaps their NCCL all-gathers with compute)
-import os as _os
-
-OVERLAP_VIEWS = _os.environ.get("BMKG_OVERLAP_VIEWS", "0") == "1"      # measured on 4 x B200 (cfg4): 32.5 -> 32.4 ms, the all-gather kernels then compete with the compute for SMs
-_VIEW_STREAMS: dict = {}
-
-
-def _view_streams(device, n):
-    key = (torch.device(device).index, n)
-    if key not in _VIEW_STREAMS:
-        _VIEW_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
-    return _VIEW_STREAMS[key]
 
 
 def allreduce_grads(params, group=None):
