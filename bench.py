@@ -516,12 +516,16 @@ def run_ours(args, rank, world, local_rank):
     # (pinned-memory prefetch, as a DataLoader with pin_memory does); all copies are inside the timed region.
     k2_warm = 2 if (args.e2e_steps is None or args.e2e_steps > 1) else 1
     copy_stream = torch.cuda.Stream(device=dev)
-    x_src = x_host
-    if full_shard:   # a sharded loader moves only this rank's node block of the features (edge_index stays replicated)
-        from biomedkg_b200.dist import shard_layout
+    x_src, ei_src = x_host, ei_host
+    if full_shard:   # a sharded loader: every rank reads its node block of the features and 1/world of the edge list from the host
+        from biomedkg_b200.dist import edge_chunk, gather_edge_index, shard_layout
 
         b0, b1 = shard_layout(N, world)[1][rank]
         x_src = x_host[b0:b1].contiguous().pin_memory()
+        per, c0, c1 = edge_chunk(E, world, rank)
+        ei_src = torch.zeros(2, per, dtype=torch.int64)
+        ei_src[:, : c1 - c0] = ei_host[:, c0:c1]
+        ei_src = ei_src.pin_memory()
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
@@ -529,7 +533,7 @@ def run_ours(args, rank, world, local_rank):
             bt.x = x_src.to(dev, non_blocking=True)
             if full_shard:
                 bt.num_nodes = N
-            bt.edge_index = ei_host.to(dev, non_blocking=True)
+            bt.edge_index = ei_src.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return bt, ev
@@ -558,6 +562,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.current_stream().wait_event(ev)
             bt.x.record_stream(torch.cuda.current_stream())
             bt.edge_index.record_stream(torch.cuda.current_stream())
+            if full_shard:      # the edge-list chunks of all ranks -> the full int64 [2, E] edge_index, over NVLink
+                bt.edge_index = gather_edge_index(bt.edge_index, E)
             if i + 1 < k:
                 nxt = prefetch()
             losses_host[i:i + 1].copy_(run_e2e(bt).detach().reshape(1), non_blocking=True)   # device -> host read of the loss, every step
@@ -577,14 +583,15 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    h2d = x_src.numel() * 4 + ei_host.numel() * 8
+    h2d = x_src.numel() * 4 + ei_src.numel() * 8
     ht = torch.tensor([float(h2d)], device=dev)
     if world > 1:
         dist.all_reduce(ht)                                  # bytes copied by all ranks per step
     e2e = {"value": nodes_total / (e2e_ms * 1e-3), "unit": "nodes/s", "h2d_bytes_per_step": int(ht.item()),
            "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms,
            "note": "pinned-host batch copied every step (prefetched one step ahead on a copy stream; row-sharded ranks copy their own node block of "
-                   "x and the whole edge_index), edge_index re-sorted every step, loss copied to pinned host memory every step (async), one sync at the end"
+                   "x and 1/N of the int64 edge_index, which is then all-gathered over NVLink), edge_index re-sorted every step, loss copied to pinned "
+                   "host memory every step (async), one sync at the end"
                    + ("; forward+backward (incl. the sort) replayed from a CUDA graph over static input buffers" if e2e_graph else "")}
 
     clocks = sampler.stop((wall0, wall1), (wall2, wall3)) if rank == 0 else None    # both timed regions (device-resident and end-to-end)

@@ -356,6 +356,24 @@ def sharded_grace_loss(module, x, edge_index, group=None, num_nodes=None):
     return sharded_infonce_local(model.project(z1), model.project(z2), N, tau, group)
 
 
+def edge_chunk(num_edges: int, world: int, rank: int):
+    """Column range of edge_index a sharded loader reads on ``rank`` (equal chunks; the last may be short)."""
+    per = (num_edges + world - 1) // world
+    return per, min(rank * per, num_edges), min((rank + 1) * per, num_edges)
+
+
+def gather_edge_index(chunk: torch.Tensor, num_edges: int, group=None) -> torch.Tensor:
+    """Sharded loader, graph side: every rank brings ``per`` columns of the int64 [2, E] edge_index (its ``edge_chunk``,
+    zero-padded to ``per``) and the full edge list is assembled over NVLink - E x 16 bytes cross the host's PCIe links ONCE per
+    step instead of once per rank (cfg4 on 8 GPUs: 128 MB instead of 1 GB)."""
+    world = dist.get_world_size(group)
+    per = chunk.size(1)
+    out = torch.empty(2, world * per, dtype=chunk.dtype, device=chunk.device)
+    dist.all_gather_into_tensor(out[0], chunk[0].contiguous(), group=group)
+    dist.all_gather_into_tensor(out[1], chunk[1].contiguous(), group=group)
+    return out if world * per == num_edges else out[:, :num_edges].contiguous()
+
+
 def allreduce_grads(params, group=None):
     """Sum the per-rank partial parameter gradients (one flat NCCL all-reduce)."""
     ps = [p for p in params if p.grad is not None]
