@@ -28,4 +28,11 @@ these restatements, runs them on seeded inputs and commits the outputs under
 must reproduce those vectors, and the closed forms are cross-checked against
 the as-written mask-materialising forms and against dense hand-computable
 graphs in ``tests/test_oracle.py``.
+
+``oracle/emu.py`` is the same GRACE step with bf16 rounding inserted exactly where
+the CUDA path stores bf16 (each point switchable): it separates kernel exactness
+(device vs emulation) from the cost of the storage format (emulation vs fp64) and
+is pinned to ``oracle/models.py`` with every rounding point off
+(``tests/test_emulation.py``).  ``pygcl.infonce_l2l_blockwise`` evaluates the
+closed form in row blocks so that the full-size BASELINE configurations fit.
 """
