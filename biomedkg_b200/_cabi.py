@@ -59,7 +59,7 @@ SIGNATURES = {
     "bmkg_colsum": (I, [P, P, I64, I, P, P, SZ, P]),
     "bmkg_center_cast": (I, [P, P, I64, I, P, P]),
     "bmkg_l2norm_colsum": (I, [P, I64, I, P, P, P, SZ, P]),
-    "bmkg_center_scale": (I, [P, P, P, I64, I, F, P, P, P, P]),
+    "bmkg_center_scale": (I, [P, P, P, I64, I, F, P, P, P]),
     "bmkg_l2norm_scale_bwd": (I, [P, P, P, I64, I, F, P, P]),
     "bmkg_colmean_sigmoid": (I, [P, I64, I, P, P, SZ, P]),
     "bmkg_rowdot": (I, [P, P, I64, I, P, P]),
@@ -87,11 +87,12 @@ SIGNATURES = {
     "bmkg_infonce_padded_rows": (I64, [I64, I64]),
     "bmkg_infonce_workspace_bytes": (SZ, [I64, I]),
     "bmkg_infonce_e_store_bytes": (SZ, [I64, I64, I64, I64]),
+    "bmkg_infonce_ext": (I, [P, I64, I64, P, P]),
     "bmkg_infonce_fwd": (I, [P, P, P, I64, I, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd": (I, [P, P, P, P, P, I64, I, P, P]),
+    "bmkg_infonce_bwd": (I, [P, P, P, P, P, P, I64, I, P, P]),
     "bmkg_infonce_workspace_bytes_rows": (SZ, [I64, I64, I, I64, I64]),
     "bmkg_infonce_fwd_rows": (I, [P, P, P, I64, I64, I, I64, I64, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, I64, I64, I, I64, I64, P, P]),
+    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, P, I64, I64, I, I64, I64, P, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -99,7 +100,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-if lib.bmkg_abi_version() != 2:
+if lib.bmkg_abi_version() != 3:
     raise ImportError("libbmkg_b200.so ABI version mismatch; rebuild with `python biomedkg_b200/build.py --force`")
 
 #: number of kernel-launching C-ABI calls made so far (bench.py reports it as gpu_launches evidence)
@@ -129,7 +130,7 @@ KERNELS_PER_CALL = {
     "bmkg_csr_filter": 6, "bmkg_gcn_aggregate": 1, "bmkg_gcn_aggregate_rows": 1, "bmkg_gcn_star_aggregate": 1, "bmkg_mask_cast": 1, "bmkg_modality_mean": 1,
     "bmkg_relu_dropout_bwd": 2, "bmkg_colsum": 2, "bmkg_linear_nt": 1, "bmkg_linear_tn": 2, "bmkg_center_cast": 1, "bmkg_l2norm_colsum": 2, "bmkg_center_scale": 1, "bmkg_l2norm_scale_bwd": 1,
     "bmkg_colmean_sigmoid": 3, "bmkg_rowdot": 1, "bmkg_rowdot_bwd": 1, "bmkg_softplus_pair_sum": 2,
-    "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_fwd": 3,
+    "bmkg_softplus_pair_bwd": 1, "bmkg_fusion_attn_fwd": 1, "bmkg_fusion_attn_bwd": 1, "bmkg_infonce_ext": 1, "bmkg_infonce_fwd": 3,
     "bmkg_infonce_bwd": 1, "bmkg_infonce_fwd_rows": 3, "bmkg_infonce_bwd_rows": 1, "bmkg_gat_scores": 1, "bmkg_gat_aggregate": 1, "bmkg_gat_aggregate_bwd": 2, "bmkg_mask_cast_bwd": 1, "bmkg_colsum_bf16": 3,
     "bmkg_redaf_fwd": 1, "bmkg_redaf_bwd": 1, "bmkg_sample_count": 3, "bmkg_sample_pick": 1, "bmkg_sample_relabel": 6,
     "bmkg_sample_set_ids": 1,

@@ -287,8 +287,7 @@ __global__ void __launch_bounds__(256) l2norm_colsum_kernel(const float* __restr
 // pass 2: d_u = bf16(h_u * inv_norm[u] * scale - mu), a_u = mu . d_u (of the ROUNDED deviation, fp32)
 __global__ void __launch_bounds__(256) center_scale_kernel(const float* __restrict__ h, const float* __restrict__ inv_norm,
                                                            const float* __restrict__ mu, int64_t N, int D, float scale,
-                                                           __nv_bfloat16* __restrict__ z, float* __restrict__ a,
-                                                           float* __restrict__ w) {
+                                                           __nv_bfloat16* __restrict__ z, float* __restrict__ a) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= N) return;
@@ -307,10 +306,7 @@ __global__ void __launch_bounds__(256) center_scale_kernel(const float* __restri
     dot = fmaf(m.w, __uint_as_float(hi & 0xffff0000u), dot);
   }
   dot = warp_sum(dot);
-  if (lane == 0) {
-    a[row] = dot;
-    w[row] = exp2f(dot);
-  }
+  if (lane == 0) a[row] = dot;
 }
 
 // dh = scale * inv * (dz - u (u . dz)),  u = h * inv   (straight-through the bf16 rounding)
@@ -476,11 +472,11 @@ int bmkg_l2norm_colsum(const float* h, int64_t N, int D, float* inv_norm, float*
 }
 
 int bmkg_center_scale(const float* h, const float* inv_norm, const float* mu, int64_t N, int D, float scale, void* z_bf16,
-                      float* a, float* w, void* stream) {
-  BMKG_REQUIRE(h && inv_norm && mu && z_bf16 && a && w && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
+                      float* a, void* stream) {
+  BMKG_REQUIRE(h && inv_norm && mu && z_bf16 && a && N > 0 && D > 0 && D % 4 == 0, BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(aligned16(h) && aligned16(z_bf16) && aligned16(mu), BMKG_ERR_MISALIGNED);
   center_scale_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      h, inv_norm, mu, N, D, scale, static_cast<__nv_bfloat16*>(z_bf16), a, w);
+      h, inv_norm, mu, N, D, scale, static_cast<__nv_bfloat16*>(z_bf16), a);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }

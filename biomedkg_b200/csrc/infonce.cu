@@ -16,10 +16,11 @@
 // Centred operand.  Z is stored as a common fp32 vector mu plus bf16 deviations d_u = z_u - mu (bmkg_center_scale), because
 // near-collapsed embeddings (initialisation, over-smoothing) differ only at the 1e-3 level, below bf16 resolution:
 //      z_u . z_v = d_u . d_v + a_u + a_v + |mu|^2,     a_u = mu . d_u  (fp32)
-// The tensor core contracts the deviations; a_v is added per column before ex2 and the row factor 2^(a_u + |mu|^2) is
-// taken out of the sum:  R_u = 2^(a_u + |mu|^2) R'_u,  R'_u = sum_{v != u} 2^(d_u . d_v + a_v).  |mu|^2 cancels in the loss:
-//      loss = (1/2N) [ sum_u ln R'_u - ln2 sum_u a_u - 2 ln2 sum_i d_i . d_{N+i} ]
-// and with q_u = 1/R'_u, w_u = 2^(a_u) the backward weights are  P_uv = 2^(d_u . d_v) (q_u w_v + q_v w_u)  (symmetric),
+// The tensor core contracts the deviations AND adds the two rank-1 terms: every operand row carries 16 extra K columns
+// ("ext", bmkg_infonce_ext: a split into three bf16 pieces next to three ones), so ONE extra K = 16 tcgen05.mma step per
+// tile (1/16 of the tile's tensor work) leaves  S''_uv = d_u . d_v + a_u + a_v  in the fp32 accumulator and the softmax
+// warps run the plain ex2 + add of the uncentred kernel.  |mu|^2 is never needed: with R''_u = sum_{v != u} 2^(S''_uv)
+//      loss = (1/2N) [ sum_u ln R''_u - 2 ln2 sum_i S''_{i, pair(i)} ],     P_uv = 2^(S''_uv) (t_u + t_v),  t = 1 / R''  (symmetric),
 //      dZ_u = (ln2/2N) [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ].
 // bf16 P only ever multiplies deviations; the common part rides on fp32 row sums.  mu = 0 gives the plain formulation.
 //
@@ -52,11 +53,13 @@ constexpr int kTmemCols = 512;
 // forward: 3 stages of (128 rows x 512 B).  The stationary row block (A) lives in TMEM, not smem: the SS form would re-read
 // it from shared memory for every MMA and the kernel is smem-bandwidth bound.
 constexpr int kFwdStages = 3, kFwdAcc = 3, kFwdPanelBytes = kBN * 128;
-constexpr size_t kFwdSmemBytes = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStages + 256;
+constexpr int kExtBytes = kBM * 32;          // ext tile: 128 rows x 16 bf16 (32-byte swizzle rows), 4 KB
+constexpr size_t kFwdSmemBytes = 1024 + ((size_t)kFwdPanelBytes * kMaxPanels + kExtBytes) * kFwdStages + kExtBytes + 256;
 constexpr int kETileBytes = kBM * kBN * 2;   // one stored tile of E = 2^S (bf16): 32 KB
 // stored-E forward: 2 column-tile stages + one E staging tile per softmax warpgroup (written out by a TMA bulk store)
 constexpr int kFwdStagesStore = 2;
-constexpr size_t kFwdSmemBytesStore = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * kFwdStagesStore + 2 * (size_t)kETileBytes + 256;
+constexpr size_t kFwdSmemBytesStore =
+    1024 + ((size_t)kFwdPanelBytes * kMaxPanels + kExtBytes) * kFwdStagesStore + 2 * (size_t)kETileBytes + kExtBytes + 256;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -119,9 +122,9 @@ __device__ __forceinline__ void stage_rows_to_tmem(const __nv_bfloat16* __restri
 // TMEM map: [0,128) stationary rows A (bf16), [128 + 128 i, +128) accumulator ring i = 0..2.
 template <int NP, bool STORE>  // NP = D / 64 (number of 64-column K panels), compile-time so the MMA issue loop fully unrolls
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule sch, int rows_padded,
-                   const __nv_bfloat16* __restrict__ z, const float* __restrict__ w /*[rows_padded] 2^a_v, 1 for padding*/,
-                   float* __restrict__ partial, uint8_t* __restrict__ e_store /*nullable: bf16 2^S tiles for the backward*/) {
+infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_x /*ext [rows_padded, 32]*/,
+                   int rows, Schedule sch, int rows_padded, const __nv_bfloat16* __restrict__ z, float* __restrict__ partial,
+                   uint8_t* __restrict__ e_store /*nullable: bf16 2^S'' tiles for the backward*/) {
   constexpr int D = NP * kPanelElems;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -129,10 +132,13 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   constexpr int kStages = STORE ? kFwdStagesStore : kFwdStages;
   uint8_t* sB = smem;
   uint8_t* sE = smem + (size_t)kFwdPanelBytes * kMaxPanels * kStages;   // STORE: [2 warpgroups][32 KB] E staging tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (STORE ? 2 * kETileBytes : 0));
+  uint8_t* sXB = sE + (STORE ? 2 * kETileBytes : 0);                    // [kStages][4 KB] ext columns of the column tiles
+  uint8_t* sXA = sXB + (size_t)kStages * kExtBytes;                     // [4 KB] ext columns of the stationary rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXA + kExtBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = full + kStages;            // [kStages]
-  uint64_t* a_full = empty + kStages;          // stationary rows staged in TMEM (4 warp arrivals)
+  uint64_t* xa_full = empty + kStages;         // ext tile of the stationary rows landed
+  uint64_t* a_full = xa_full + 1;              // stationary rows staged in TMEM (4 warp arrivals)
   uint64_t* a_empty = a_full + 1;              // every MMA of the work item retired
   uint64_t* tfull = a_empty + 1;               // [kFwdAcc]
   uint64_t* tempty = tfull + kFwdAcc;          // [kFwdAcc]
@@ -145,10 +151,12 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     ptx::mbar_init(a_full, 4);
+    ptx::mbar_init(xa_full, 1);
     ptx::mbar_init(a_empty, 1);
     for (int b = 0; b < kFwdAcc; ++b) { ptx::mbar_init(&tfull[b], 1); ptx::mbar_init(&tempty[b], 4); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmap);
+    ptx::prefetch_tensormap(&tmap_x);
   }
   if (warp == 0) ptx::tmem_alloc<kTmemCols>(tmem_slot);
   ptx::tc_fence_before();
@@ -160,18 +168,24 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   const uint32_t tile_bytes = (uint32_t)npanels * kFwdPanelBytes;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer: column tiles only ----------------
+    if (lane == 0) {  // ---------------- TMA producer: column tiles (+ their ext columns), ext columns of the stationary rows ----------------
       int stage = 0;
-      uint32_t sphase = 0;
+      uint32_t sphase = 0, aphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = sch.rb0 + item % sch.nrb;
         const int cc = item / sch.nrb;  // chunk-major: all CTAs sweep the same column chunk together (L2-resident)
+        ptx::mbar_wait(a_empty, aphase ^ 1);     // the previous item's MMAs (which read sXA) have retired
+        aphase ^= 1;
+        ptx::mbar_arrive_expect_tx(xa_full, (uint32_t)kExtBytes);
+        ptx::tma_load_2d(sXA, &tmap_x, xa_full, 0, rb * kBM);            // ext columns [0,16): the A-side layout (1,1,1,a_hi,a_mid,a_lo,..)
         const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
         for (int ct = t0; ct < t1; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes + (uint32_t)kExtBytes);
           uint8_t* dst = sB + (size_t)stage * kFwdPanelBytes * kMaxPanels;
           for (int p = 0; p < npanels; ++p)
             ptx::tma_load_2d(dst + p * kFwdPanelBytes, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          ptx::tma_load_2d(sXB + (size_t)stage * kExtBytes, &tmap_x, &full[stage], 16, ct * kBN);   // ext columns [16,32): the B-side layout
           if (++stage == kStages) { stage = 0; sphase ^= 1; }
         }
       }
@@ -184,8 +198,10 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int cc = item / sch.nrb;  // chunk-major: all CTAs sweep the same column chunk together (L2-resident)
         ptx::mbar_wait(a_full, aphase);
+        ptx::mbar_wait(xa_full, aphase);
         aphase ^= 1;
         ptx::tc_fence_after();
+        const uint64_t xadesc = ptx::smem_desc_sw32(ptx::smem_u32(sXA));
         const int t0 = cc * sch.tiles_per_chunk, t1 = min(sch.ntiles, t0 + sch.tiles_per_chunk);
         for (int ct = t0; ct < t1; ++ct) {
           ptx::mbar_wait(&tempty[acc], accphase ^ 1);
@@ -194,12 +210,14 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           // one descriptor per stage, advanced per K step by a compile-time constant (start-address field, 16 B units):
           // keeps the single issuing thread at a few instructions per tcgen05.mma
           const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + (size_t)stage * kFwdPanelBytes * kMaxPanels), 16, 1024);
+          const uint64_t xbdesc = ptx::smem_desc_sw32(ptx::smem_u32(sXB + (size_t)stage * kExtBytes));
           const uint32_t d_tmem = tmem_base + 128u + (uint32_t)acc * kBN;
           if (ptx::elect_one()) {
+            ptx::umma_ss(d_tmem, xadesc, xbdesc, idesc, 0u);     // the ext K step: a_u + a_v (both operands from shared memory)
 #pragma unroll
             for (int kk = 0; kk < NP * 4; ++kk) {
               const uint32_t off16 = (uint32_t)(((kk >> 2) * kFwdPanelBytes + (kk & 3) * 32) >> 4);
-              ptx::umma_ts(d_tmem, tmem_base + (uint32_t)kk * 8u, bdesc + off16, idesc, kk > 0 ? 1u : 0u);
+              ptx::umma_ts(d_tmem, tmem_base + (uint32_t)kk * 8u, bdesc + off16, idesc, 1u);
             }
             ptx::umma_commit(&empty[stage]);
             ptx::umma_commit(&tfull[acc]);
@@ -242,7 +260,6 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
         const bool diag = (ct == rb);
         // 128 columns in 4 chunks of 32, loads issued two chunks ahead of the exp/sum so TMEM latency is hidden
         uint32_t ra[32], rb_[32];
-        const float4* wvp = reinterpret_cast<const float4*>(w + (size_t)ct * kBN);   // w_v = 2^a_v of this tile's columns (lane-uniform)
         // stored-E mode: this thread's row of the tile, 16 B (8 columns) at a time, chunk-major inside the 32 KB tile
         // (offset = chunk * 2048 + row * 16: conflict-free st.shared here and conflict-free LDS.128 in the backward).  The tile
         // is staged in this warpgroup's shared-memory buffer and leaves through ONE asynchronous bulk store, so the
@@ -260,17 +277,12 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            // 2^(S + a_v) = 2^S w_v: the column factor rides on the accumulate (one packed FFMA per two elements) and the
-            // load is off the ex2 dependency chain
-            const float4 wa = __ldg(wvp + c * 8 + (j >> 2)), wb = __ldg(wvp + c * 8 + (j >> 2) + 1);
             const float2 e01 = ex2_pair(r[j], r[j + 1], BMKG_POLY_FWD >= 3);
             const float2 e23 = ex2_pair(r[j + 2], r[j + 3], BMKG_POLY_FWD >= 2);
             const float2 e45 = ex2_pair(r[j + 4], r[j + 5], BMKG_POLY_FWD >= 4);
             const float2 e67 = ex2_pair(r[j + 6], r[j + 7], BMKG_POLY_FWD >= 1);
-            s01 = __ffma2_rn(e01, make_float2(wa.x, wa.y), s01);
-            s23 = __ffma2_rn(e23, make_float2(wa.z, wa.w), s23);
-            s01 = __ffma2_rn(e45, make_float2(wb.x, wb.y), s01);
-            s23 = __ffma2_rn(e67, make_float2(wb.z, wb.w), s23);
+            s01 = __fadd2_rn(s01, __fadd2_rn(e01, e45));       // packed fp32x2 adds: one instruction per two elements
+            s23 = __fadd2_rn(s23, __fadd2_rn(e23, e67));
             if (STORE)
               *reinterpret_cast<uint4*>(etile + (size_t)(c * 4 + (j >> 3)) * 2048) =
                   make_uint4(pack2(e01.x, e01.y), pack2(e23.x, e23.y), pack2(e45.x, e45.y), pack2(e67.x, e67.y));
@@ -308,12 +320,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, int rows, Schedule 
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// R'_u, q_u = 1/R'_u, w_u = 2^(a_u), and the loss terms ln R'_u - ln2 a_u - 2 ln2 d_i . d_{N+i}; fixed-order block partials.
+// R''_u, t_u = 1/R''_u and the loss terms ln R''_u - 2 ln2 S''_{i,pair(i)} (view-1 rows); fixed-order block partials.
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
                                                                     int row_begin, int row_end, int rows_pad_end, int N, int B, int D, float npad,
                                                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ a,
-                                                                    const float* __restrict__ w, float* __restrict__ qw,
-                                                                    float* __restrict__ block_part) {
+                                                                    float* __restrict__ t, float* __restrict__ block_part) {
   __shared__ float red[8];
   const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, row_end) are this launch's
   float term = 0.f;
@@ -323,11 +334,9 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
   if (u < row_end && (blk >> 1) * B + (u - blk * B) < N) {
     float R = 0.f;
     for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
-    R -= npad;                      // zero-filled out-of-range columns have w_v = 1 and contributed exactly 1.0 each
-    // qw: per PAIR of rows (q_2k, q_2k+1, w_2k, w_2k+1), so the backward's packed fp32x2 math loads register pairs directly
-    qw[(u >> 1) * 4 + (u & 1)] = 1.0f / R;
-    qw[(u >> 1) * 4 + 2 + (u & 1)] = w[u];
-    term = logf(R) - 0.6931471805599453f * a[u];
+    R -= npad;                      // all-zero columns (layout padding, TMA out-of-range fill) have S'' = 0 and contributed exactly 1.0 each
+    t[u] = 1.0f / R;
+    term = logf(R);
     if ((blk & 1) == 0) {   // view-1 row: positive pair with the same node's view-2 row
       const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
       const uint4* zb = reinterpret_cast<const uint4*>(z + (size_t)(u + B) * D);
@@ -339,19 +348,18 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
 #pragma unroll
         for (int i = 0; i < 8; ++i) dot = fmaf(fa[i], fb[i], dot);
       }
-      term -= 2.0f * 0.6931471805599453f * dot;
+      term -= 2.0f * 0.6931471805599453f * (dot + a[u] + a[u + B]);
     }
   } else if (u < rows_pad_end) {
-    qw[(u >> 1) * 4 + (u & 1)] = 0.f;
-    qw[(u >> 1) * 4 + 2 + (u & 1)] = 0.f;
+    t[u] = 0.f;
   }
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    block_part[blockIdx.x] = t;
+    float tt = 0.f;
+    for (int w = 0; w < 8; ++w) tt += red[w];
+    block_part[blockIdx.x] = tt;
   }
 }
 __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_part, int nb, float inv_2n, float* __restrict__ loss) {
@@ -371,13 +379,15 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
 // may be issued into the buffer MMA2(t) still reads without waiting for MMA2(t) to complete.
 constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
-constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
+constexpr size_t kBwdSmemBytesA =
+    1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + (size_t)kExtBytes * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
-                   const float* __restrict__ qw /*[>= ntiles*128][2]: (q, q, w, w) per row pair, zero padded*/, const float* __restrict__ mu /*[D]*/,
-                   const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z, float* __restrict__ dz) {
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_x /*ext [rows_padded, 32]*/, int N, int B,
+                   int rb0, int nrb, int ntiles, const float* __restrict__ t /*[>= ntiles*128] 1/R'', zero padded*/,
+                   const float* __restrict__ mu /*[D]*/, const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z,
+                   float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
   extern __shared__ uint8_t smem_raw[];
@@ -385,7 +395,9 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kPB * kMaxPanels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
+  uint8_t* sXA = smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA);   // [4 KB] ext columns of the stationary rows
+  uint8_t* sXB = sXA + kExtBytes;                                       // [2][4 KB] ext columns of the V tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXB + (size_t)kBwdStagesA * kExtBytes);
   uint64_t* full = bars;                    // [2] V tile landed
   uint64_t* empty = full + 2;               // [2] V tile no longer needed (MMA2 done)
   uint64_t* a_full = empty + 2;
@@ -395,13 +407,14 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   uint64_t* dz_full = p_full + 8;
   uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
-  float* s_rowsum = reinterpret_cast<float*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA) + 256);   // [2 warpgroups][128 rows]
+  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 warpgroups][128 rows]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -429,14 +442,16 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       uint32_t sphase = 0, aphase = 0;
       for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_empty, aphase ^ 1);
-        ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
+        ptx::mbar_arrive_expect_tx(a_full, tile_bytes + (uint32_t)kExtBytes);
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
+        ptx::tma_load_2d(sXA, &tmap_x, a_full, 0, rb * kBM);             // ext columns [0,16): A-side layout
         aphase ^= 1;
         for (int ct = 0; ct < ntiles; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes + (uint32_t)kExtBytes);
           uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
           for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          ptx::tma_load_2d(sXB + (size_t)stage * kExtBytes, &tmap_x, &full[stage], 16, ct * kBN);   // ext columns [16,32): B-side layout
           if (++stage == kBwdStagesA) { stage = 0; sphase ^= 1; }
         }
       }
@@ -446,11 +461,13 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T   (A, B K-major in smem)
       constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);    // dZ += P Z_V     (A tmem, B MN-major)
       const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA), 16, 1024);
-      uint64_t bdesc_k[2], bdesc_mn[2];  // per stage: K-major view (MMA1) and MN-major view (MMA2) of the same tile
+      const uint64_t xadesc = ptx::smem_desc_sw32(ptx::smem_u32(sXA));
+      uint64_t bdesc_k[2], bdesc_mn[2], xbdesc[2];  // per stage: K-major view (MMA1), MN-major view (MMA2) of the same tile, its ext columns
       for (int st = 0; st < 2; ++st) {
         const uint32_t a = ptx::smem_u32(sB + (size_t)st * kPB * kMaxPanels);
         bdesc_k[st] = ptx::smem_desc_sw128(a, 16, 1024);
         bdesc_mn[st] = ptx::smem_desc_sw128(a, kPB, 1024);
+        xbdesc[st] = ptx::smem_desc_sw32(ptx::smem_u32(sXB + (size_t)st * kExtBytes));
       }
       uint32_t tcount = 0;  // global tile counter of this CTA: stage = buffer = tcount & 1, phase = (tcount >> 1) & 1
       uint32_t aphase = 0, dzphase = 0;
@@ -461,10 +478,11 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         const uint32_t d_tmem = tmem_base + kColS + b * 128u;
         const uint64_t bd = bdesc_k[b];
         if (ptx::elect_one()) {
+          ptx::umma_ss(d_tmem, xadesc, xbdesc[b], idesc1, 0u);   // the ext K step: a_u + a_v
 #pragma unroll
           for (int kk = 0; kk < NP * 4; ++kk) {
             const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
-            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, 1u);
           }
           ptx::umma_commit(&s_full[b]);
         }
@@ -528,8 +546,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
     uint32_t tcount = 0, dzphase = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float qu = __ldg(qw + (row >> 1) * 4 + (row & 1)), wu = __ldg(qw + (row >> 1) * 4 + 2 + (row & 1));   // zeros for padding rows
-      const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
+      const float tu = __ldg(t + row);          // 1/R''_u; zero for padding rows
+      const float2 tu2 = make_float2(tu, tu);
       const int colbase = wg * 64;
       float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
@@ -537,8 +555,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        const float4* cvp = reinterpret_cast<const float4*>(qw + 2 * gcol0);   // (q_v, q_v+1, w_v, w_v+1): one float4 = two columns
-        float4 cvr[16];  // first 32 columns: fetched before the wait so the load latency is off the S -> P chain
+        const float4* cvp = reinterpret_cast<const float4*>(t + gcol0);
+        float4 cvr[16];  // 1/R'' of this tile's columns: fetched before the wait so the load latency is off the S -> P chain
 #pragma unroll
         for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
         ptx::mbar_wait(&s_full[b], ph);
@@ -548,16 +566,13 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         ptx::tmem_ld32(taddr + 32, r1);
         ptx::tmem_ld_wait();
         const bool diag = (row >= gcol0) && (row < gcol0 + 64);
-        // P_uv = 2^S (q_u w_v + q_v w_u)
+        // P_uv = 2^S'' (t_u + t_v), packed fp32x2: two columns per instruction
         auto make_p = [&](const uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 c01 = cvr[2 * q], c23 = cvr[2 * q + 1];
-            // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
-            const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
-            const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
-            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), t01);
-            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), t23);
+            const float4 cv = cvr[c * 8 + q];
+            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), __fadd2_rn(tu2, make_float2(cv.x, cv.y)));
+            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), __fadd2_rn(tu2, make_float2(cv.z, cv.w)));
             if (diag) {
               const int j = gcol0 + c * 32 + 4 * q;
               if (j + 0 == row) p01.x = 0.f;
@@ -572,8 +587,6 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         };
         uint32_t pk[16];
         make_p(r0, 0, pk);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 16 + q);   // second 32 columns (L1-resident, lane-uniform)
         ptx::tmem_st16(taddr, pk);  // P (bf16 pairs) aliases this warpgroup's own, already consumed, S columns
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -591,7 +604,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       // before every softmax warp has arrived on dz_empty, i.e. after its read below).
       s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;
+      // all-zero columns (layout padding, out-of-range fill) have S'' = 0 and t_v = 0: each added exactly t_u to the row sum
+      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - (float)(ntiles * kBN - 2 * N) * tu - 2.0f;
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
@@ -653,7 +667,7 @@ constexpr size_t kBwdESmemBytes = 1024 + 2 * (size_t)kFwdPanelBytes * kMaxPanels
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
-                     const float* __restrict__ qw, const float* __restrict__ mu, const float* __restrict__ gscale,
+                     const float* __restrict__ t, const float* __restrict__ mu, const float* __restrict__ gscale,
                      const __nv_bfloat16* __restrict__ z, const uint8_t* __restrict__ e_store, float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
@@ -765,16 +779,16 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
     uint32_t tcount = 0, dzphase = 0, es = 0, eph = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float qu = __ldg(qw + (row >> 1) * 4 + (row & 1)), wu = __ldg(qw + (row >> 1) * 4 + 2 + (row & 1));   // zeros for padding rows
-      const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
+      const float tu = __ldg(t + row);          // 1/R''_u; zero for padding rows
+      const float2 tu2 = make_float2(tu, tu);
       const int colbase = wg * 64;
       float2 psum = make_float2(0.f, 0.f);
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;
-        const float4* cvp = reinterpret_cast<const float4*>(qw + 2 * gcol0);   // (q_v, q_v+1, w_v, w_v+1): one float4 = two columns
-        float4 cvr[16];
+        const float4* cvp = reinterpret_cast<const float4*>(t + gcol0);
+        float4 cvr[16];   // 1/R'' of this warpgroup's 64 columns
 #pragma unroll
         for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
         ptx::mbar_wait(&e_full[es], eph);
@@ -789,12 +803,13 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
             const uint4 u = ev[c * 4 + i];
             const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {   // two columns per 32-bit word
-              const float4 cv = cvr[i * 4 + h];
-              const float2 t = __ffma2_rn(qu2, make_float2(cv.z, cv.w), __fmul2_rn(make_float2(cv.x, cv.y), wu2));
-              const float2 p = __fmul2_rn(make_float2(__uint_as_float(wds[h] << 16), __uint_as_float(wds[h] & 0xffff0000u)), t);
-              psum = __fadd2_rn(psum, p);
-              pk[i * 4 + h] = pack2(p.x, p.y);
+            for (int h = 0; h < 4; h += 2) {   // two columns per 32-bit word, four per float4 of t
+              const float4 cv = cvr[c * 8 + i * 2 + (h >> 1)];
+              const float2 p01 = __fmul2_rn(make_float2(__uint_as_float(wds[h] << 16), __uint_as_float(wds[h] & 0xffff0000u)), __fadd2_rn(tu2, make_float2(cv.x, cv.y)));
+              const float2 p23 = __fmul2_rn(make_float2(__uint_as_float(wds[h + 1] << 16), __uint_as_float(wds[h + 1] & 0xffff0000u)), __fadd2_rn(tu2, make_float2(cv.z, cv.w)));
+              psum = __fadd2_rn(psum, __fadd2_rn(p01, p23));
+              pk[i * 4 + h] = pack2(p01.x, p01.y);
+              pk[i * 4 + h + 1] = pack2(p23.x, p23.y);
             }
           }
         };
@@ -802,8 +817,6 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
         ptx::mbar_wait(&p_empty[b], ph ^ 1);   // MMA2 of the tile that used this P buffer two tiles ago has retired
         ptx::tc_fence_after();
         make_p(0, pk);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 16 + q);
         ptx::tmem_st16(taddr, pk);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -821,7 +834,8 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
       }
       s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;
+      // all-zero columns (layout padding, out-of-range fill) have S'' = 0 and t_v = 0: each added exactly t_u to the row sum
+      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - (float)(ntiles * kBN - 2 * N) * tu - 2.0f;
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
@@ -866,6 +880,28 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ext columns of every stacked row: xab[u] = [ A-side: 1,1,1, a_hi,a_mid,a_lo, 0 x10 | B-side: a_hi,a_mid,a_lo, 1,1,1, 0 x10 ] (bf16),
+// a_u = a_hi + a_mid + a_lo to ~2^-24 relative, so that <A-side(u), B-side(v)> = a_u + a_v in the fp32 accumulator.  Rows of
+// padding nodes (and beyond the stacked rows) are all zero: their S'' stays exactly 0.
+__global__ void __launch_bounds__(256) infonce_ext_kernel(const float* __restrict__ a, int N, int B, int rows_padded, uint4* __restrict__ xab) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= rows_padded) return;
+  const int blk = u / B;
+  uint4 o[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+  if ((blk >> 1) * B + (u - blk * B) < N) {
+    const float av = a[u];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(av);
+    const float r1 = av - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    const uint32_t one = 0x3f80u, h = __bfloat16_as_ushort(hi), m = __bfloat16_as_ushort(mid), l = __bfloat16_as_ushort(lo);
+    o[0] = make_uint4(one | (one << 16), one | (h << 16), m | (l << 16), 0u);     // A side: 1, 1, 1, hi, mid, lo, 0, 0
+    o[2] = make_uint4(h | (m << 16), l | (one << 16), one | (one << 16), 0u);     // B side: hi, mid, lo, 1, 1, 1, 0, 0
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xab[(size_t)u * 4 + i] = o[i];
+}
+
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
@@ -899,6 +935,21 @@ static int make_z_tensormap(CUtensorMap* m, const void* z, int64_t rows, int D, 
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(z), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) g_last_driver_status = (int)r;
+  return r == CUDA_SUCCESS ? BMKG_OK : BMKG_ERR_DRIVER;
+}
+
+// ext columns: bf16 [rows_padded, 32] row-major; box = 16 columns (32 B) x 128 rows, 32-byte swizzle
+static int make_x_tensormap(CUtensorMap* m, const void* xab, int64_t rows_padded) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return BMKG_ERR_DRIVER;
+  cuuint64_t gdim[2] = {32u, (cuuint64_t)rows_padded};
+  cuuint64_t gstride[1] = {64u};
+  cuuint32_t box[2] = {16u, (cuuint32_t)kBM};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(xab), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) g_last_driver_status = (int)r;
   return r == CUDA_SUCCESS ? BMKG_OK : BMKG_ERR_DRIVER;
@@ -975,8 +1026,20 @@ size_t bmkg_infonce_e_store_bytes(int64_t N, int64_t B, int64_t row_begin, int64
   return (size_t)ceil_div(row_end - row_begin, kBM) * (size_t)ceil_div(rows, kBN) * kETileBytes;
 }
 
-int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, int64_t N, int64_t B, int D, int64_t row_begin,
-                          int64_t row_end, float* loss, float* qw, void* e_store, void* ws, size_t ws_bytes, void* stream) {
+int bmkg_infonce_ext(const float* a, int64_t N, int64_t B, void* xab_bf16, void* stream) {
+  BMKG_REQUIRE(a && xab_bf16 && block_ok(N, B), BMKG_ERR_BAD_ARG);
+  BMKG_REQUIRE(aligned16(xab_bf16), BMKG_ERR_MISALIGNED);
+  const int64_t rp = bmkg_infonce_padded_rows(N, B);
+  infonce_ext_kernel<<<(unsigned)ceil_div(rp, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, (int)N, (int)B, (int)rp,
+                                                                                               static_cast<uint4*>(xab_bf16));
+  BMKG_CHECK_LAUNCH();
+  return BMKG_OK;
+}
+
+int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf16, int64_t N, int64_t B, int D, int64_t row_begin,
+                          int64_t row_end, float* loss, float* t, void* e_store, void* ws, size_t ws_bytes, void* stream) {
+  const void* w = xab_bf16;
+  float* qw = t;
   BMKG_REQUIRE(z_bf16 && a && w && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(w) && aligned16(qw) && aligned16(e_store), BMKG_ERR_MISALIGNED);
@@ -992,8 +1055,10 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
   const int nb = (int)ceil_div(rp, 256);
   float* block_part = c.take<float>(nb);
 
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_x;
   int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
+  if (rc != BMKG_OK) return rc;
+  rc = make_x_tensormap(&tmap_x, xab_bf16, rp);
   if (rc != BMKG_OK) return rc;
   const int n_items = s.nrb * s.nchunks;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
@@ -1002,11 +1067,11 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
   {                                                                                                                   \
     if (e_store) {                                                                                                    \
       if (!set_smem(infonce_fwd_kernel<NP_, true>, kFwdSmemBytesStore)) return BMKG_ERR_LAUNCH;                       \
-      infonce_fwd_kernel<NP_, true><<<grid, kThreads, kFwdSmemBytesStore, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, \
+      infonce_fwd_kernel<NP_, true><<<grid, kThreads, kFwdSmemBytesStore, st>>>(tmap, tmap_x, (int)rows, s, (int)rp, zp, partial, \
                                                                                 static_cast<uint8_t*>(e_store));      \
     } else {                                                                                                          \
       if (!set_smem(infonce_fwd_kernel<NP_, false>, kFwdSmemBytes)) return BMKG_ERR_LAUNCH;                           \
-      infonce_fwd_kernel<NP_, false><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, (int)rows, s, (int)rp, zp, w, partial, nullptr); \
+      infonce_fwd_kernel<NP_, false><<<grid, kThreads, kFwdSmemBytes, st>>>(tmap, tmap_x, (int)rows, s, (int)rp, zp, partial, nullptr); \
     }                                                                                                                 \
   }
   switch (D / kPanelElems) {
@@ -1022,20 +1087,21 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, in
   const int64_t pad_end = (row_end == rows) ? rp : row_end;
   const int nbr = (int)ceil_div(pad_end - row_begin, 256);
   infonce_finalize_rows_kernel<<<nbr, 256, 0, st>>>(partial, nslots, (int)rp, (int)row_begin, (int)row_end, (int)pad_end, (int)N,
-                                                    (int)B, D, npad, zp, a, w, qw, block_part);
+                                                    (int)B, D, npad, zp, a, t, block_part);
   infonce_finalize_loss_kernel<<<1, 32, 0, st>>>(block_part, nbr, 1.0f / (2.0f * (float)N), loss);
   BMKG_CHECK_LAUNCH();
   return BMKG_OK;
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t N, int D, float* loss, float* qw, void* e_store,
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t N, int D, float* loss, float* t, void* e_store,
                      void* ws, size_t ws_bytes, void* stream) {
-  return bmkg_infonce_fwd_rows(z_bf16, a, w, N, N, D, 0, 2 * N, loss, qw, e_store, ws, ws_bytes, stream);
+  return bmkg_infonce_fwd_rows(z_bf16, a, xab_bf16, N, N, D, 0, 2 * N, loss, t, e_store, ws, ws_bytes, stream);
 }
 
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store, int64_t N,
-                          int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
-  BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
+                          const void* xab_bf16, int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
+  const float* qw = t;
+  BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && xab_bf16 && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu) && aligned16(e_store), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1043,8 +1109,10 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
   const int rb0 = (int)(row_begin / kBM);
   const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, kBN);
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_x;
   int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
+  if (rc != BMKG_OK) return rc;
+  rc = make_x_tensormap(&tmap_x, xab_bf16, bmkg_infonce_padded_rows(N, B));
   if (rc != BMKG_OK) return rc;
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
@@ -1069,7 +1137,7 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
 #define BMKG_LAUNCH_BWD(NP_)                                                                                        \
   {                                                                                                                 \
     if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \
-    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
+    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, tmap_x, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_BWD(1) break;
@@ -1082,9 +1150,9 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, 
   return BMKG_OK;
 }
 
-int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store, int64_t N, int D,
-                     float* dz, void* stream) {
-  return bmkg_infonce_bwd_rows(z_bf16, qw, mu, gscale, e_store, N, N, D, 0, 2 * N, dz, stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store, const void* xab_bf16,
+                     int64_t N, int D, float* dz, void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, t, mu, gscale, e_store, xab_bf16, N, N, D, 0, 2 * N, dz, stream);
 }
 
 }  // extern "C"

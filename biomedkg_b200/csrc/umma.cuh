@@ -165,6 +165,16 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same with the 32-byte swizzle (layout type 6): K-major tiles whose rows are 32 bytes (16 bf16), 8-row groups 256 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset: unused for swizzled K-major operands
+  d |= (uint64_t)(256 >> 4) << 32;   // stride byte offset: 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate.
 //   [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)
 //   [15] a_major (0=K,1=MN)  [16] b_major  [17,23) N>>3  [24,29) M>>4

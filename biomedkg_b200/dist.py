@@ -9,7 +9,7 @@ Rank p owns the nodes [pB, (p+1)B) in BOTH views, so
   * InfoNCE: the stacked operand uses the block-interleaved layout of include/bmkg_b200.h with view block B - one
     all-gather of every rank's [2, B, D] block assembles it, and a rank's rows of both views are one contiguous 128-aligned
     range [2pB, 2(p+1)B).  forward: all-reduce of the [D] column sums (common vector mu), all-gather of the bf16
-    deviations Z and of a = mu . d, the row-range tcgen05 kernel, all-gather of (q, w) (2 floats per row), all-reduce of the
+    deviations Z and of a = mu . d, the row-range tcgen05 kernel, all-gather of t = 1/R'' (1 float per row), all-reduce of the
     scalar loss share.  backward: the row-range kernel writes dZ of exactly the rows whose h this rank holds - NO collective.
   * parameter gradients are partial sums over the rank's rows -> one flat all-reduce (``allreduce_grads``).
 
@@ -64,46 +64,42 @@ class CudaImpl:
         D = hs[0].size(1)
         z = torch.zeros(2, B, D, dtype=torch.bfloat16, device=mu.device)
         a = torch.zeros(2, B, dtype=torch.float32, device=mu.device)
-        w = torch.empty(2, B, dtype=torch.float32, device=mu.device)      # scratch: the gathered w is recomputed as 2^a
         for v, (h, inv) in enumerate(zip(hs, invs)):
             if h.size(0) > 0:
-                call("bmkg_center_scale", _p(h), _p(inv), _p(mu), h.size(0), D, scale, _p(z[v]), _p(a[v]), _p(w[v]), _stream())
+                call("bmkg_center_scale", _p(h), _p(inv), _p(mu), h.size(0), D, scale, _p(z[v]), _p(a[v]), _stream())
         return z, a
 
     def fwd_rows(self, Z, A, N, B, r0, r1):
-        """Z bf16 [R_all, D], A fp32 [R_all] -> (loss share, qw [R_all, 2] with rows [r0, r1) filled)"""
-        from .ops import _p, _stream, _ws, call, lib
+        """Z bf16 [R_all, D], A fp32 [R_all] (gathered) -> (loss share, t = 1/R'' [R_all] with rows [r0, r1) filled)"""
+        from .ops import _p, _stream, _ws, alloc_e_store, call, lib
 
         D = Z.size(1)
-        rp = int(lib.bmkg_infonce_padded_rows(N, B))      # the kernels read a / write qw in whole 128-row tiles
+        rp = int(lib.bmkg_infonce_padded_rows(N, B))      # the kernels read a / write t in whole 128-row tiles
         if A.numel() < rp:
             raise ValueError(f"a must hold bmkg_infonce_padded_rows = {rp} entries (zero beyond the stacked rows), got {A.numel()}")
         loss = torch.zeros((), dtype=torch.float32, device=Z.device)
-        qw = torch.zeros(max(Z.size(0), rp), 2, dtype=torch.float32, device=Z.device)
-        self.e_store = None
+        t = torch.zeros(max(Z.size(0), rp), dtype=torch.float32, device=Z.device)
+        self.e_store = self.xab = None
         if r1 > r0:
-            from .ops import alloc_e_store
-
-            W = torch.exp(A * 0.6931471805599453)            # 2^a (not torch.exp2: a jiterator kernel, NVRTC-compiled at run time); padding: a = 0 -> w = 1
+            self.xab = torch.empty(rp, 32, dtype=torch.bfloat16, device=Z.device)       # ext K columns of EVERY row, from the gathered a
+            call("bmkg_infonce_ext", _p(A), N, B, _p(self.xab), _stream())
             ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
-            self.e_store = alloc_e_store(N, B, r0, r1, Z.device)      # E = 2^S of this rank's rows, kept for the backward if it fits
-            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(W), N, B, D, r0, r1, _p(loss), _p(qw), _p(self.e_store), _p(ws), ws.numel(),
+            self.e_store = alloc_e_store(N, B, r0, r1, Z.device)      # E = 2^S'' of this rank's rows, kept for the backward if enabled
+            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(self.xab), N, B, D, r0, r1, _p(loss), _p(t), _p(self.e_store), _p(ws), ws.numel(),
                  _stream())
-        return loss, qw
+        return loss, t
 
-    def bwd_rows(self, Z, QW, mu, g, N, B, r0, r1):
+    def bwd_rows(self, Z, T, mu, g, N, B, r0, r1):
         """-> dZ fp32 [r1 - r0, D] of this range (the kernel addresses dz by global row: pass the buffer shifted by -r0 rows)"""
-        from .ops import _p, _stream, call, lib
+        from .ops import _p, _stream, call, lib, release_e_store
 
         D = Z.size(1)
-        if QW.size(0) < int(lib.bmkg_infonce_padded_rows(N, B)):
-            raise ValueError("qw must hold bmkg_infonce_padded_rows rows (zeros for padding rows)")
+        if T.numel() < int(lib.bmkg_infonce_padded_rows(N, B)):
+            raise ValueError("t must hold bmkg_infonce_padded_rows entries (zeros for padding rows)")
         dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
         if r1 > r0:
-            call("bmkg_infonce_bwd_rows", _p(Z), _p(QW), _p(mu), _p(g), _p(getattr(self, "e_store", None)), N, B, D, r0, r1,
+            call("bmkg_infonce_bwd_rows", _p(Z), _p(T), _p(mu), _p(g), _p(getattr(self, "e_store", None)), _p(self.xab), N, B, D, r0, r1,
                  dz.data_ptr() - r0 * D * 4, _stream())
-            from .ops import release_e_store
-
             release_e_store(getattr(self, "e_store", None))
             self.e_store = None
         return dz
@@ -144,9 +140,9 @@ class _ShardedInfoNCEFn(torch.autograd.Function):
         dist.all_gather_into_tensor(A, ab.view(2 * B), group=group)
         nblk = (N + B - 1) // B
         r0, r1 = (rank * 2 * B, (rank + 1) * 2 * B) if rank < nblk else (0, 0)
-        loss, qw = impl.fwd_rows(Z, A, N, B, r0, r1)
-        QW = torch.empty(R_all, 2, dtype=qw.dtype, device=dev)
-        dist.all_gather_into_tensor(QW, qw[rank * 2 * B: (rank + 1) * 2 * B].contiguous(), group=group)
+        loss, t = impl.fwd_rows(Z, A, N, B, r0, r1)
+        QW = torch.empty((R_all,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)      # the per-row forward -> backward state of every rank
+        dist.all_gather_into_tensor(QW, t[rank * 2 * B: (rank + 1) * 2 * B].contiguous(), group=group)
         dist.all_reduce(loss, group=group)
         ctx.save_for_backward(h1, h2, inv1, inv2, Z, QW, mu)
         ctx.meta = (scale, impl, N, B, r0, r1)

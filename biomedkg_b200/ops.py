@@ -767,7 +767,7 @@ class _InfoNCEFn(torch.autograd.Function):
         rp = int(lib.bmkg_infonce_padded_rows(N, N))
         z = torch.empty(2 * N, D, dtype=BF16, device=dev)
         a = torch.zeros(rp, dtype=torch.float32, device=dev)
-        w = torch.ones(rp, dtype=torch.float32, device=dev)
+        xab = torch.empty(rp, 32, dtype=BF16, device=dev)     # ext K columns: the tensor core adds a_u + a_v (bmkg_infonce_ext)
         inv_norm = torch.empty(2 * N, dtype=torch.float32, device=dev)
         cs = torch.empty(2, D, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_colsum_workspace_bytes(N, D), dev)
@@ -775,25 +775,26 @@ class _InfoNCEFn(torch.autograd.Function):
         call("bmkg_l2norm_colsum", _p(h2), N, D, inv_norm.data_ptr() + N * 4, _p(cs[1]), _p(ws), ws.numel(), _stream())
         # common vector of the centred representation z_u = mu + d_u: the column mean of the normalised, scaled rows
         mu = cs.sum(0) * (scale / (2.0 * N)) if CENTER_INFONCE else torch.zeros(D, dtype=torch.float32, device=dev)
-        call("bmkg_center_scale", _p(h1), _p(inv_norm), _p(mu), N, D, scale, _p(z), _p(a), _p(w), _stream())
+        call("bmkg_center_scale", _p(h1), _p(inv_norm), _p(mu), N, D, scale, _p(z), _p(a), _stream())
         call("bmkg_center_scale", _p(h2), inv_norm.data_ptr() + N * 4, _p(mu), N, D, scale, z.data_ptr() + N * D * 2,
-             a.data_ptr() + N * 4, w.data_ptr() + N * 4, _stream())
+             a.data_ptr() + N * 4, _stream())
+        call("bmkg_infonce_ext", _p(a), N, N, _p(xab), _stream())
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        qw = torch.empty(rp, 2, dtype=torch.float32, device=dev)
+        t = torch.empty(rp, dtype=torch.float32, device=dev)
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
         e_store = alloc_e_store(N, N, 0, 2 * N, dev) if any(ctx.needs_input_grad[:2]) else None      # only a backward reads it
-        call("bmkg_infonce_fwd", _p(z), _p(a), _p(w), N, D, _p(loss), _p(qw), _p(e_store), _p(ws), ws.numel(), _stream())
-        ctx.save_for_backward(h1, h2, z, inv_norm, qw, mu, e_store)
+        call("bmkg_infonce_fwd", _p(z), _p(a), _p(xab), N, D, _p(loss), _p(t), _p(e_store), _p(ws), ws.numel(), _stream())
+        ctx.save_for_backward(h1, h2, z, inv_norm, t, mu, e_store, xab)
         ctx.scale = scale
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        h1, h2, z, inv_norm, qw, mu, e_store = ctx.saved_tensors
+        h1, h2, z, inv_norm, t, mu, e_store, xab = ctx.saved_tensors
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        call("bmkg_infonce_bwd", _p(z), _p(qw), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _stream())
+        call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), _p(xab), N, D, _p(dz), _stream())
         release_e_store(e_store)
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())

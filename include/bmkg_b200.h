@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BMKG_ABI_VERSION 2
+#define BMKG_ABI_VERSION 3
 
 int bmkg_abi_version(void);
 /* last CUresult (or 100000 + cudaError*100 + query status) seen while building a TMA tensor map; 0 = none */
@@ -151,7 +151,7 @@ int bmkg_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* colind, const i
  *   (GCL/losses/infonce.py, called from gcl_module.py:189) fused with the sqrt(log2e/tau) scale, in the centred
  *   representation the InfoNCE kernels consume:  z_u = mu + d_u  with a common fp32 vector mu [D] and bf16 deviations.
  *     l2norm_colsum: inv_norm[u] = 1/max(|h_u|, 1e-12), colsum[c] = sum_u h[u,c] * inv_norm[u]   (caller: mu = colsum * scale / rows)
- *     center_scale : d_u = bf16(h_u * inv_norm[u] * scale - mu), a[u] = mu . d_u (fp32), w[u] = 2^a[u]
+ *     center_scale : d_u = bf16(h_u * inv_norm[u] * scale - mu), a[u] = mu . d_u (fp32)
  *   mu may be any vector (all zeros = the plain normalised rows); the column mean makes d small when embeddings are similar. */
 int bmkg_mask_cast(const float* x, const uint8_t* keep1, const uint8_t* keep2, int64_t n, void* x0_bf16, void* x1_bf16,
                    void* x2_bf16, void* stream);
@@ -175,7 +175,7 @@ int bmkg_center_cast(const float* x, const float* m, int64_t num_rows, int chann
 int bmkg_l2norm_colsum(const float* h, int64_t num_rows, int dim, float* inv_norm, float* colsum, void* ws, size_t ws_bytes,
                        void* stream);   /* ws >= bmkg_colsum_workspace_bytes(num_rows, dim); dim <= 1024 */
 int bmkg_center_scale(const float* h, const float* inv_norm, const float* mu, int64_t num_rows, int dim, float scale,
-                      void* z_bf16, float* a, float* w, void* stream);
+                      void* z_bf16, float* a, void* stream);
 int bmkg_l2norm_scale_bwd(const float* h, const float* inv_norm, const float* dz, int64_t num_rows, int dim, float scale,
                           float* dh, void* stream);
 
@@ -237,38 +237,41 @@ int bmkg_linear_tn(const void* g_bf16, const void* x_bf16, const float* addend, 
 /* ---- I1/I2: fused GRACE InfoNCE (tcgen05 / TMEM / TMA) -----------------------------------
  * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).
  * Operand (bmkg_center_scale): z bf16 [R, D] holds the DEVIATIONS d_u of the normalised, sqrt(log2e/tau)-scaled rows from a
- * common fp32 vector mu [D]; a fp32 [P] = mu . d_u and w fp32 [P] = 2^a.  D in {64,128,192,256}.
+ * common fp32 vector mu [D]; a fp32 [P] = mu . d_u; xab bf16 [P, 32] (bmkg_infonce_ext) = 16 + 16 extra K columns per row that make
+ * the tensor core add a_u + a_v to d_u . d_v (one extra K = 16 MMA step per tile).  D in {64,128,192,256}.
  * Block-interleaved stacked layout with view block B (B == N: one block, i.e. [h1 rows; h2 rows]; otherwise B % 128 == 0):
  *   rows [2kB, 2kB+B) = view 1 (h1) of nodes [kB, kB+B), rows [2kB+B, 2kB+2B) = view 2 (h2) of the same nodes, k < ceil(N/B);
  *   R = bmkg_infonce_stacked_rows(N, B) = 2 B ceil(N/B); rows of nodes >= N are ZERO in z and a; P = bmkg_infonce_padded_rows(N, B)
- *   (R rounded up to 128); beyond R and for padding rows a is ZERO and w is ONE.  With B = the node block of one rank, a rank's rows of both views are ONE
+ *   (R rounded up to 128) and a is zero beyond R.  With B = the node block of one rank, a rank's rows of both views are ONE
  *   contiguous, 128-aligned range - the unit of the row-sharded multi-GPU path.
- * fwd writes the scalar loss and qw fp32 [P][2], an opaque hand-over to bwd: per pair of rows (q_2k, q_2k+1, w_2k, w_2k+1) with
- * q_u = 1/R'_u, R'_u = sum_{v != u} 2^(d_u.d_v + a_v) (zeros for padding rows); bwd writes dL/dz fp32 [R, D] (valid rows only) scaled by *gscale:
- *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],  P_uv = 2^(d_u.d_v) (q_u w_v + q_v w_u).
+ * fwd writes the scalar loss and t fp32 [P] = 1 / R''_u, R''_u = sum_{v != u} 2^(d_u.d_v + a_u + a_v) (zero for padding rows);
+ * bwd writes dL/dz fp32 [R, D] (valid rows only) scaled by *gscale:
+ *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],  P_uv = 2^(d_u.d_v + a_u + a_v) (t_u + t_v).
  * Optional E store: pass e_store (bmkg_infonce_e_store_bytes bytes, 16-byte aligned; NULL = off) to fwd and the SAME buffer to
- * bwd: the forward then also writes E = 2^(d_u.d_v) as bf16 tiles and the backward streams them back instead of recomputing
- * the similarities (16 N^2 D -> 8 N^2 D executed; 8 N^2 bytes of HBM per full-range launch - the caller decides whether it fits). */
+ * bwd: the forward then also writes E = 2^(d_u.d_v + a_u + a_v) as bf16 tiles and the backward streams them back instead of
+ * recomputing the similarities (16 N^2 D -> 8 N^2 D executed; 8 N^2 bytes of HBM per full-range launch - the caller decides). */
 int64_t bmkg_infonce_stacked_rows(int64_t num_nodes, int64_t view_block);
 size_t bmkg_infonce_e_store_bytes(int64_t num_nodes, int64_t view_block, int64_t row_begin, int64_t row_end);
 int64_t bmkg_infonce_padded_rows(int64_t num_nodes, int64_t view_block);
 size_t bmkg_infonce_workspace_bytes(int64_t num_nodes, int dim);
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, const float* w, int64_t num_nodes, int dim, float* loss, float* qw,
+/* xab[u] = [1,1,1,a_hi,a_mid,a_lo,0.. | a_hi,a_mid,a_lo,1,1,1,0..] (a split into three bf16 pieces) for valid rows, zeros otherwise */
+int bmkg_infonce_ext(const float* a, int64_t num_nodes, int64_t view_block, void* xab_bf16, void* stream);
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int dim, float* loss, float* t,
                      void* e_store, void* ws, size_t ws_bytes, void* stream);
-int bmkg_infonce_bwd(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store,
-                     int64_t num_nodes, int dim, float* dz, void* stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
+                     const void* xab_bf16, int64_t num_nodes, int dim, float* dz, void* stream);
 /* Row-range variants: only rows [row_begin, row_end) of the stacked matrix are processed against ALL columns.
  * row_begin % 128 == 0; row_end % 128 == 0 or row_end == R.  fwd_rows writes this range's share of the loss (the shares of
- * all ranges add up to the loss) and qw for the range; bwd_rows needs qw for all rows (all-gathered) and writes dz rows of
+ * all ranges add up to the loss) and t for the range; bwd_rows needs t for all rows (all-gathered) and writes dz rows of
  * the range (dz is addressed with the GLOBAL row index: pass the base of an [R, D] array, or a pointer offset by
  * -row_begin * D elements for a range-local buffer). */
 size_t bmkg_infonce_workspace_bytes_rows(int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end);
-int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const float* w, int64_t num_nodes, int64_t view_block, int dim,
-                          int64_t row_begin, int64_t row_end, float* loss, float* qw, void* e_store, void* ws, size_t ws_bytes,
+int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int64_t view_block, int dim,
+                          int64_t row_begin, int64_t row_end, float* loss, float* t, void* e_store, void* ws, size_t ws_bytes,
                           void* stream);
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* qw, const float* mu, const float* gscale, const void* e_store,
-                          int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end, float* dz,
-                          void* stream);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
+                          const void* xab_bf16, int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end,
+                          float* dz, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,19 +73,20 @@ def test_lightning_stand_in_captures_outermost_init_kwargs():
     assert "model" not in m.hparams and "embed_dim" not in m.hparams        # BaseGCL's own arguments are not the checkpoint's
 
 
-def test_graphed_step_refuses_objectives_with_host_side_draws():
+def test_graphed_step_host_side_draws_contract():
+    """GGD's augmentation coin is a host branch: GraphedStep wants one capture per branch (graphed_step does that); every
+    module then fails loudly on CPU tensors - there is no CPU path to capture."""
     import pytest
 
     import biomedkg_b200 as b
-    from biomedkg_b200.graphed import GraphedStep
+    from biomedkg_b200.graphed import GraphedStep, graphed_step
 
-    for cls in (b.DGIModule, b.GGDModule):
-        m = cls(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2)
-        with pytest.raises(NotImplementedError):
-            GraphedStep(m, torch.zeros(8, 32), torch.zeros(2, 4, dtype=torch.int64))
-    with pytest.raises(RuntimeError):      # GRACE passes the objective check and then fails loudly on CPU tensors (no CPU path)
-        GraphedStep(b.GRACEModule(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2), torch.zeros(8, 32),
-                    torch.zeros(2, 4, dtype=torch.int64))
+    x, ei = torch.zeros(8, 32), torch.zeros(2, 4, dtype=torch.int64)
+    with pytest.raises(ValueError):
+        GraphedStep(b.GGDModule(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2), x, ei)
+    for cls in (b.DGIModule, b.GGDModule, b.GRACEModule):
+        with pytest.raises(RuntimeError):
+            graphed_step(cls(in_dim=32, hidden_dim=64, out_dim=64, num_hidden_layers=2), x, ei)
 
 
 def test_sampler_structure_checker_accepts_oracle_and_rejects_corruptions():
