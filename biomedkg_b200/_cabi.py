@@ -89,10 +89,10 @@ SIGNATURES = {
     "bmkg_infonce_e_store_bytes": (SZ, [I64, I64, I64, I64]),
     "bmkg_infonce_ext": (I, [P, I64, I64, P, P]),
     "bmkg_infonce_fwd": (I, [P, P, P, I64, I, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd": (I, [P, P, P, P, P, P, I64, I, P, P]),
+    "bmkg_infonce_bwd": (I, [P, P, P, P, P, I64, I, P, P]),
     "bmkg_infonce_workspace_bytes_rows": (SZ, [I64, I64, I, I64, I64]),
     "bmkg_infonce_fwd_rows": (I, [P, P, P, I64, I64, I, I64, I64, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, P, I64, I64, I, I64, I64, P, P]),
+    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, I64, I64, I, I64, I64, P, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

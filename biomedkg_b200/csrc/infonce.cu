@@ -324,7 +324,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float* __restrict__ partial, int nslots, int rows_padded,
                                                                     int row_begin, int row_end, int rows_pad_end, int N, int B, int D, float npad,
                                                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ a,
-                                                                    float* __restrict__ t, float* __restrict__ block_part) {
+                                                                    float* __restrict__ st /*[P/2][8]: q,q,w,w,t,t,0,0 per row pair*/,
+                                                                    float* __restrict__ block_part) {
   __shared__ float red[8];
   const int u = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, row_end) are this launch's
   float term = 0.f;
@@ -335,7 +336,13 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
     float R = 0.f;
     for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
     R -= npad;                      // all-zero columns (layout padding, TMA out-of-range fill) have S'' = 0 and contributed exactly 1.0 each
-    t[u] = 1.0f / R;
+    // forward -> backward state, per PAIR of rows (q, q, w, w, t, t, 0, 0): t = 1/R'', w = 2^a, q = t w, so that
+    // P_uv = 2^(S''_uv) (t_u + t_v) = 2^(d_u.d_v) (q_u w_v + q_v w_u); packed so the backward's fp32x2 math loads register pairs
+    const float tv = 1.0f / R, wv = exp2f(a[u]);
+    float* sp = st + (size_t)(u >> 1) * 8 + (u & 1);
+    sp[0] = tv * wv;
+    sp[2] = wv;
+    sp[4] = tv;
     term = logf(R);
     if ((blk & 1) == 0) {   // view-1 row: positive pair with the same node's view-2 row
       const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
@@ -351,7 +358,14 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
       term -= 2.0f * 0.6931471805599453f * (dot + a[u] + a[u + B]);
     }
   } else if (u < rows_pad_end) {
-    t[u] = 0.f;
+    float* sp = st + (size_t)(u >> 1) * 8 + (u & 1);
+    sp[0] = 0.f;
+    sp[2] = 0.f;
+    sp[4] = 0.f;
+  }
+  if (u < rows_pad_end && (u & 1) == 0) {   // the two unused floats of the pair
+    st[(size_t)(u >> 1) * 8 + 6] = 0.f;
+    st[(size_t)(u >> 1) * 8 + 7] = 0.f;
   }
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
@@ -379,13 +393,12 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
 // may be issued into the buffer MMA2(t) still reads without waiting for MMA2(t) to complete.
 constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
-constexpr size_t kBwdSmemBytesA =
-    1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + (size_t)kExtBytes * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
+constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
 
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_x /*ext [rows_padded, 32]*/, int N, int B,
-                   int rb0, int nrb, int ntiles, const float* __restrict__ t /*[>= ntiles*128] 1/R'', zero padded*/,
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
+                   const float* __restrict__ st /*[>= ntiles*64][8]: (q,q,w,w,t,t,0,0) per row pair, zero padded*/,
                    const float* __restrict__ mu /*[D]*/, const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z,
                    float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
@@ -395,9 +408,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kPB * kMaxPanels;
-  uint8_t* sXA = smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA);   // [4 KB] ext columns of the stationary rows
-  uint8_t* sXB = sXA + kExtBytes;                                       // [2][4 KB] ext columns of the V tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXB + (size_t)kBwdStagesA * kExtBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
   uint64_t* full = bars;                    // [2] V tile landed
   uint64_t* empty = full + 2;               // [2] V tile no longer needed (MMA2 done)
   uint64_t* a_full = empty + 2;
@@ -414,7 +425,6 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
   constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
-    ptx::prefetch_tensormap(&tmap_x);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
@@ -442,16 +452,14 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       uint32_t sphase = 0, aphase = 0;
       for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
         ptx::mbar_wait(a_empty, aphase ^ 1);
-        ptx::mbar_arrive_expect_tx(a_full, tile_bytes + (uint32_t)kExtBytes);
+        ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
-        ptx::tma_load_2d(sXA, &tmap_x, a_full, 0, rb * kBM);             // ext columns [0,16): A-side layout
         aphase ^= 1;
         for (int ct = 0; ct < ntiles; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes + (uint32_t)kExtBytes);
+          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
           uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
           for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBN);
-          ptx::tma_load_2d(sXB + (size_t)stage * kExtBytes, &tmap_x, &full[stage], 16, ct * kBN);   // ext columns [16,32): B-side layout
           if (++stage == kBwdStagesA) { stage = 0; sphase ^= 1; }
         }
       }
@@ -461,13 +469,11 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T   (A, B K-major in smem)
       constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);    // dZ += P Z_V     (A tmem, B MN-major)
       const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA), 16, 1024);
-      const uint64_t xadesc = ptx::smem_desc_sw32(ptx::smem_u32(sXA));
-      uint64_t bdesc_k[2], bdesc_mn[2], xbdesc[2];  // per stage: K-major view (MMA1), MN-major view (MMA2) of the same tile, its ext columns
-      for (int st = 0; st < 2; ++st) {
-        const uint32_t a = ptx::smem_u32(sB + (size_t)st * kPB * kMaxPanels);
-        bdesc_k[st] = ptx::smem_desc_sw128(a, 16, 1024);
-        bdesc_mn[st] = ptx::smem_desc_sw128(a, kPB, 1024);
-        xbdesc[st] = ptx::smem_desc_sw32(ptx::smem_u32(sXB + (size_t)st * kExtBytes));
+      uint64_t bdesc_k[2], bdesc_mn[2];  // per stage: K-major view (MMA1) and MN-major view (MMA2) of the same tile
+      for (int sg = 0; sg < 2; ++sg) {
+        const uint32_t a = ptx::smem_u32(sB + (size_t)sg * kPB * kMaxPanels);
+        bdesc_k[sg] = ptx::smem_desc_sw128(a, 16, 1024);
+        bdesc_mn[sg] = ptx::smem_desc_sw128(a, kPB, 1024);
       }
       uint32_t tcount = 0;  // global tile counter of this CTA: stage = buffer = tcount & 1, phase = (tcount >> 1) & 1
       uint32_t aphase = 0, dzphase = 0;
@@ -478,11 +484,10 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t d_tmem = tmem_base + kColS + b * 128u;
         const uint64_t bd = bdesc_k[b];
         if (ptx::elect_one()) {
-          ptx::umma_ss(d_tmem, xadesc, xbdesc[b], idesc1, 0u);   // the ext K step: a_u + a_v
 #pragma unroll
           for (int kk = 0; kk < NP * 4; ++kk) {
             const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
-            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, 1u);
+            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
           }
           ptx::umma_commit(&s_full[b]);
         }
@@ -546,8 +551,11 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint32_t tcount = 0, dzphase = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float tu = __ldg(t + row);          // 1/R''_u; zero for padding rows
-      const float2 tu2 = make_float2(tu, tu);
+      // S = d_u . d_v here (no ext K step: in this kernel the extra MMA costs more than the packed ALU it saves, measured);
+      // the rank-1 terms enter through  P_uv = 2^S (q_u w_v + q_v w_u),  q = t w,  w = 2^a
+      const float* su = st + (size_t)(row >> 1) * 8 + (row & 1);
+      const float qu = __ldg(su), wu = __ldg(su + 2), tu = __ldg(su + 4);   // zeros for padding rows
+      const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
       const int colbase = wg * 64;
       float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
       for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
@@ -555,10 +563,10 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        const float4* cvp = reinterpret_cast<const float4*>(t + gcol0);
-        float4 cvr[16];  // 1/R'' of this tile's columns: fetched before the wait so the load latency is off the S -> P chain
+        const float4* cvp = reinterpret_cast<const float4*>(st + (size_t)gcol0 * 4);   // (q, q, w, w) of a column pair every 8 floats
+        float4 cvr[16];  // first 32 columns: fetched before the wait so the load latency is off the S -> P chain
 #pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 2 * q);
         ptx::mbar_wait(&s_full[b], ph);
         ptx::tc_fence_after();
         uint32_t r0[32], r1[32];
@@ -566,13 +574,15 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         ptx::tmem_ld32(taddr + 32, r1);
         ptx::tmem_ld_wait();
         const bool diag = (row >= gcol0) && (row < gcol0 + 64);
-        // P_uv = 2^S'' (t_u + t_v), packed fp32x2: two columns per instruction
         auto make_p = [&](const uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 cv = cvr[c * 8 + q];
-            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), __fadd2_rn(tu2, make_float2(cv.x, cv.y)));
-            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), __fadd2_rn(tu2, make_float2(cv.z, cv.w)));
+            const float4 c01 = cvr[2 * q], c23 = cvr[2 * q + 1];
+            // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
+            const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
+            const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
+            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), t01);
+            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), t23);
             if (diag) {
               const int j = gcol0 + c * 32 + 4 * q;
               if (j + 0 == row) p01.x = 0.f;
@@ -587,6 +597,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         };
         uint32_t pk[16];
         make_p(r0, 0, pk);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 32 + 2 * q);   // second 32 columns (L1-resident, lane-uniform)
         ptx::tmem_st16(taddr, pk);  // P (bf16 pairs) aliases this warpgroup's own, already consumed, S columns
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -604,8 +616,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       // before every softmax warp has arrived on dz_empty, i.e. after its read below).
       s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // all-zero columns (layout padding, out-of-range fill) have S'' = 0 and t_v = 0: each added exactly t_u to the row sum
-      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - (float)(ntiles * kBN - 2 * N) * tu - 2.0f;
+      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;   // all-zero columns have q_v = w_v = 0: they added nothing
+      (void)tu;
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
@@ -667,8 +679,9 @@ constexpr size_t kBwdESmemBytes = 1024 + 2 * (size_t)kFwdPanelBytes * kMaxPanels
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
-                     const float* __restrict__ t, const float* __restrict__ mu, const float* __restrict__ gscale,
-                     const __nv_bfloat16* __restrict__ z, const uint8_t* __restrict__ e_store, float* __restrict__ dz) {
+                     const float* __restrict__ st /*(q,q,w,w,t,t,0,0) per row pair*/, const float* __restrict__ mu,
+                     const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z, const uint8_t* __restrict__ e_store,
+                     float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
   constexpr int kZStage = kPB * kMaxPanels;
@@ -779,7 +792,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
     uint32_t tcount = 0, dzphase = 0, es = 0, eph = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float tu = __ldg(t + row);          // 1/R''_u; zero for padding rows
+      const float tu = __ldg(st + (size_t)(row >> 1) * 8 + 4 + (row & 1));          // 1/R''_u; zero for padding rows
       const float2 tu2 = make_float2(tu, tu);
       const int colbase = wg * 64;
       float2 psum = make_float2(0.f, 0.f);
@@ -787,10 +800,10 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;
-        const float4* cvp = reinterpret_cast<const float4*>(t + gcol0);
-        float4 cvr[16];   // 1/R'' of this warpgroup's 64 columns
+        const float* cvp = st + (size_t)gcol0 * 4 + 4;    // (t, t) of a column pair every 8 floats
+        float2 cvr[32];   // 1/R'' of this warpgroup's 64 columns
 #pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + q);
+        for (int q = 0; q < 32; ++q) cvr[q] = __ldg(reinterpret_cast<const float2*>(cvp + 8 * q));
         ptx::mbar_wait(&e_full[es], eph);
         // this thread's row, columns [64 wg, 64 wg + 64): 16-byte chunks 8 wg .. 8 wg + 7 of the chunk-major tile
         const uint4* ep = reinterpret_cast<const uint4*>(sE + (size_t)es * kETileBytes + (size_t)(wg * 8) * 2048 + (size_t)lrow * 16);
@@ -803,13 +816,11 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
             const uint4 u = ev[c * 4 + i];
             const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int h = 0; h < 4; h += 2) {   // two columns per 32-bit word, four per float4 of t
-              const float4 cv = cvr[c * 8 + i * 2 + (h >> 1)];
-              const float2 p01 = __fmul2_rn(make_float2(__uint_as_float(wds[h] << 16), __uint_as_float(wds[h] & 0xffff0000u)), __fadd2_rn(tu2, make_float2(cv.x, cv.y)));
-              const float2 p23 = __fmul2_rn(make_float2(__uint_as_float(wds[h + 1] << 16), __uint_as_float(wds[h + 1] & 0xffff0000u)), __fadd2_rn(tu2, make_float2(cv.z, cv.w)));
-              psum = __fadd2_rn(psum, __fadd2_rn(p01, p23));
-              pk[i * 4 + h] = pack2(p01.x, p01.y);
-              pk[i * 4 + h + 1] = pack2(p23.x, p23.y);
+            for (int h = 0; h < 4; ++h) {   // two columns per 32-bit word
+              const float2 p = __fmul2_rn(make_float2(__uint_as_float(wds[h] << 16), __uint_as_float(wds[h] & 0xffff0000u)),
+                                          __fadd2_rn(tu2, cvr[c * 16 + i * 4 + h]));
+              psum = __fadd2_rn(psum, p);
+              pk[i * 4 + h] = pack2(p.x, p.y);
             }
           }
         };
@@ -1037,9 +1048,10 @@ int bmkg_infonce_ext(const float* a, int64_t N, int64_t B, void* xab_bf16, void*
 }
 
 int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf16, int64_t N, int64_t B, int D, int64_t row_begin,
-                          int64_t row_end, float* loss, float* t, void* e_store, void* ws, size_t ws_bytes, void* stream) {
+                          int64_t row_end, float* loss, float* state, void* e_store, void* ws, size_t ws_bytes, void* stream) {
   const void* w = xab_bf16;
-  float* qw = t;
+  float* qw = state;
+  float* t = state;
   BMKG_REQUIRE(z_bf16 && a && w && loss && qw && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(aligned16(z_bf16) && aligned16(a) && aligned16(w) && aligned16(qw) && aligned16(e_store), BMKG_ERR_MISALIGNED);
@@ -1093,15 +1105,15 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf
   return BMKG_OK;
 }
 
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t N, int D, float* loss, float* t, void* e_store,
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t N, int D, float* loss, float* state, void* e_store,
                      void* ws, size_t ws_bytes, void* stream) {
-  return bmkg_infonce_fwd_rows(z_bf16, a, xab_bf16, N, N, D, 0, 2 * N, loss, t, e_store, ws, ws_bytes, stream);
+  return bmkg_infonce_fwd_rows(z_bf16, a, xab_bf16, N, N, D, 0, 2 * N, loss, state, e_store, ws, ws_bytes, stream);
 }
 
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
-                          const void* xab_bf16, int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
-  const float* qw = t;
-  BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && xab_bf16 && block_ok(N, B), BMKG_ERR_BAD_ARG);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store, int64_t N,
+                          int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
+  const float* qw = state;
+  BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
   BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu) && aligned16(e_store), BMKG_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1109,10 +1121,8 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, c
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);
   const int rb0 = (int)(row_begin / kBM);
   const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, kBN);
-  CUtensorMap tmap, tmap_x;
+  CUtensorMap tmap;
   int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
-  if (rc != BMKG_OK) return rc;
-  rc = make_x_tensormap(&tmap_x, xab_bf16, bmkg_infonce_padded_rows(N, B));
   if (rc != BMKG_OK) return rc;
   const int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
@@ -1137,7 +1147,7 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, c
 #define BMKG_LAUNCH_BWD(NP_)                                                                                        \
   {                                                                                                                 \
     if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \
-    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, tmap_x, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
+    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_BWD(1) break;
@@ -1150,9 +1160,9 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, c
   return BMKG_OK;
 }
 
-int bmkg_infonce_bwd(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store, const void* xab_bf16,
-                     int64_t N, int D, float* dz, void* stream) {
-  return bmkg_infonce_bwd_rows(z_bf16, t, mu, gscale, e_store, xab_bf16, N, N, D, 0, 2 * N, dz, stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store, int64_t N, int D,
+                     float* dz, void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, state, mu, gscale, e_store, N, N, D, 0, 2 * N, dz, stream);
 }
 
 }  // extern "C"

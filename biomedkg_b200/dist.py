@@ -9,7 +9,7 @@ Rank p owns the nodes [pB, (p+1)B) in BOTH views, so
   * InfoNCE: the stacked operand uses the block-interleaved layout of include/bmkg_b200.h with view block B - one
     all-gather of every rank's [2, B, D] block assembles it, and a rank's rows of both views are one contiguous 128-aligned
     range [2pB, 2(p+1)B).  forward: all-reduce of the [D] column sums (common vector mu), all-gather of the bf16
-    deviations Z and of a = mu . d, the row-range tcgen05 kernel, all-gather of t = 1/R'' (1 float per row), all-reduce of the
+    deviations Z and of a = mu . d, the row-range tcgen05 kernel, all-gather of the per-row state (4 floats per row), all-reduce of the
     scalar loss share.  backward: the row-range kernel writes dZ of exactly the rows whose h this rank holds - NO collective.
   * parameter gradients are partial sums over the rank's rows -> one flat all-reduce (``allreduce_grads``).
 
@@ -70,7 +70,7 @@ class CudaImpl:
         return z, a
 
     def fwd_rows(self, Z, A, N, B, r0, r1):
-        """Z bf16 [R_all, D], A fp32 [R_all] (gathered) -> (loss share, t = 1/R'' [R_all] with rows [r0, r1) filled)"""
+        """Z bf16 [R_all, D], A fp32 [R_all] (gathered) -> (loss share, forward->backward state [R_all, 4] with rows [r0, r1) filled)"""
         from .ops import _p, _stream, _ws, alloc_e_store, call, lib
 
         D = Z.size(1)
@@ -78,14 +78,14 @@ class CudaImpl:
         if A.numel() < rp:
             raise ValueError(f"a must hold bmkg_infonce_padded_rows = {rp} entries (zero beyond the stacked rows), got {A.numel()}")
         loss = torch.zeros((), dtype=torch.float32, device=Z.device)
-        t = torch.zeros(max(Z.size(0), rp), dtype=torch.float32, device=Z.device)
-        self.e_store = self.xab = None
+        t = torch.zeros(max(Z.size(0), rp), 4, dtype=torch.float32, device=Z.device)
+        self.e_store = None
         if r1 > r0:
-            self.xab = torch.empty(rp, 32, dtype=torch.bfloat16, device=Z.device)       # ext K columns of EVERY row, from the gathered a
-            call("bmkg_infonce_ext", _p(A), N, B, _p(self.xab), _stream())
+            xab = torch.empty(rp, 32, dtype=torch.bfloat16, device=Z.device)       # ext K columns of EVERY row, from the gathered a
+            call("bmkg_infonce_ext", _p(A), N, B, _p(xab), _stream())
             ws = _ws(lib.bmkg_infonce_workspace_bytes_rows(N, B, D, r0, r1), Z.device)
             self.e_store = alloc_e_store(N, B, r0, r1, Z.device)      # E = 2^S'' of this rank's rows, kept for the backward if enabled
-            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(self.xab), N, B, D, r0, r1, _p(loss), _p(t), _p(self.e_store), _p(ws), ws.numel(),
+            call("bmkg_infonce_fwd_rows", _p(Z), _p(A), _p(xab), N, B, D, r0, r1, _p(loss), _p(t), _p(self.e_store), _p(ws), ws.numel(),
                  _stream())
         return loss, t
 
@@ -94,11 +94,11 @@ class CudaImpl:
         from .ops import _p, _stream, call, lib, release_e_store
 
         D = Z.size(1)
-        if T.numel() < int(lib.bmkg_infonce_padded_rows(N, B)):
-            raise ValueError("t must hold bmkg_infonce_padded_rows entries (zeros for padding rows)")
+        if T.size(0) < int(lib.bmkg_infonce_padded_rows(N, B)):
+            raise ValueError("the state must hold bmkg_infonce_padded_rows rows (zeros for padding rows)")
         dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
         if r1 > r0:
-            call("bmkg_infonce_bwd_rows", _p(Z), _p(T), _p(mu), _p(g), _p(getattr(self, "e_store", None)), _p(self.xab), N, B, D, r0, r1,
+            call("bmkg_infonce_bwd_rows", _p(Z), _p(T), _p(mu), _p(g), _p(getattr(self, "e_store", None)), N, B, D, r0, r1,
                  dz.data_ptr() - r0 * D * 4, _stream())
             release_e_store(getattr(self, "e_store", None))
             self.e_store = None

@@ -780,21 +780,21 @@ class _InfoNCEFn(torch.autograd.Function):
              a.data_ptr() + N * 4, _stream())
         call("bmkg_infonce_ext", _p(a), N, N, _p(xab), _stream())
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        t = torch.empty(rp, dtype=torch.float32, device=dev)
+        t = torch.empty(rp, 4, dtype=torch.float32, device=dev)      # forward -> backward state: (q, q, w, w, t, t, 0, 0) per row pair
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
         e_store = alloc_e_store(N, N, 0, 2 * N, dev) if any(ctx.needs_input_grad[:2]) else None      # only a backward reads it
         call("bmkg_infonce_fwd", _p(z), _p(a), _p(xab), N, D, _p(loss), _p(t), _p(e_store), _p(ws), ws.numel(), _stream())
-        ctx.save_for_backward(h1, h2, z, inv_norm, t, mu, e_store, xab)
+        ctx.save_for_backward(h1, h2, z, inv_norm, t, mu, e_store)
         ctx.scale = scale
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        h1, h2, z, inv_norm, t, mu, e_store, xab = ctx.saved_tensors
+        h1, h2, z, inv_norm, t, mu, e_store = ctx.saved_tensors
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), _p(xab), N, D, _p(dz), _stream())
+        call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _stream())
         release_e_store(e_store)
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())

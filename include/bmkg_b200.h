@@ -238,15 +238,17 @@ int bmkg_linear_tn(const void* g_bf16, const void* x_bf16, const float* addend, 
  * PyGCL DualBranchContrast(InfoNCE(tau), "L2L", intraview_negs=True) (gcl_module.py:171-173,189).
  * Operand (bmkg_center_scale): z bf16 [R, D] holds the DEVIATIONS d_u of the normalised, sqrt(log2e/tau)-scaled rows from a
  * common fp32 vector mu [D]; a fp32 [P] = mu . d_u; xab bf16 [P, 32] (bmkg_infonce_ext) = 16 + 16 extra K columns per row that make
- * the tensor core add a_u + a_v to d_u . d_v (one extra K = 16 MMA step per tile).  D in {64,128,192,256}.
+ * the forward's tensor-core pass add a_u + a_v to d_u . d_v (one extra K = 16 MMA step per tile).  D in {64,128,192,256}.
  * Block-interleaved stacked layout with view block B (B == N: one block, i.e. [h1 rows; h2 rows]; otherwise B % 128 == 0):
  *   rows [2kB, 2kB+B) = view 1 (h1) of nodes [kB, kB+B), rows [2kB+B, 2kB+2B) = view 2 (h2) of the same nodes, k < ceil(N/B);
  *   R = bmkg_infonce_stacked_rows(N, B) = 2 B ceil(N/B); rows of nodes >= N are ZERO in z and a; P = bmkg_infonce_padded_rows(N, B)
  *   (R rounded up to 128) and a is zero beyond R.  With B = the node block of one rank, a rank's rows of both views are ONE
  *   contiguous, 128-aligned range - the unit of the row-sharded multi-GPU path.
- * fwd writes the scalar loss and t fp32 [P] = 1 / R''_u, R''_u = sum_{v != u} 2^(d_u.d_v + a_u + a_v) (zero for padding rows);
+ * fwd writes the scalar loss and state fp32 [P][4], an opaque hand-over to bwd: per pair of rows (q, q, w, w, t, t, 0, 0) with
+ * t_u = 1 / R''_u, R''_u = sum_{v != u} 2^(d_u.d_v + a_u + a_v), w = 2^a, q = t w (zeros for padding rows);
  * bwd writes dL/dz fp32 [R, D] (valid rows only) scaled by *gscale:
- *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],  P_uv = 2^(d_u.d_v + a_u + a_v) (t_u + t_v).
+ *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],
+ *   P_uv = 2^(d_u.d_v + a_u + a_v) (t_u + t_v) = 2^(d_u.d_v) (q_u w_v + q_v w_u).
  * Optional E store: pass e_store (bmkg_infonce_e_store_bytes bytes, 16-byte aligned; NULL = off) to fwd and the SAME buffer to
  * bwd: the forward then also writes E = 2^(d_u.d_v + a_u + a_v) as bf16 tiles and the backward streams them back instead of
  * recomputing the similarities (16 N^2 D -> 8 N^2 D executed; 8 N^2 bytes of HBM per full-range launch - the caller decides). */
@@ -256,22 +258,22 @@ int64_t bmkg_infonce_padded_rows(int64_t num_nodes, int64_t view_block);
 size_t bmkg_infonce_workspace_bytes(int64_t num_nodes, int dim);
 /* xab[u] = [1,1,1,a_hi,a_mid,a_lo,0.. | a_hi,a_mid,a_lo,1,1,1,0..] (a split into three bf16 pieces) for valid rows, zeros otherwise */
 int bmkg_infonce_ext(const float* a, int64_t num_nodes, int64_t view_block, void* xab_bf16, void* stream);
-int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int dim, float* loss, float* t,
+int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int dim, float* loss, float* state,
                      void* e_store, void* ws, size_t ws_bytes, void* stream);
-int bmkg_infonce_bwd(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
-                     const void* xab_bf16, int64_t num_nodes, int dim, float* dz, void* stream);
+int bmkg_infonce_bwd(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store,
+                     int64_t num_nodes, int dim, float* dz, void* stream);
 /* Row-range variants: only rows [row_begin, row_end) of the stacked matrix are processed against ALL columns.
  * row_begin % 128 == 0; row_end % 128 == 0 or row_end == R.  fwd_rows writes this range's share of the loss (the shares of
- * all ranges add up to the loss) and t for the range; bwd_rows needs t for all rows (all-gathered) and writes dz rows of
+ * all ranges add up to the loss) and state for the range; bwd_rows needs state for all rows (all-gathered) and writes dz rows of
  * the range (dz is addressed with the GLOBAL row index: pass the base of an [R, D] array, or a pointer offset by
  * -row_begin * D elements for a range-local buffer). */
 size_t bmkg_infonce_workspace_bytes_rows(int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end);
 int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int64_t view_block, int dim,
-                          int64_t row_begin, int64_t row_end, float* loss, float* t, void* e_store, void* ws, size_t ws_bytes,
+                          int64_t row_begin, int64_t row_end, float* loss, float* state, void* e_store, void* ws, size_t ws_bytes,
                           void* stream);
-int bmkg_infonce_bwd_rows(const void* z_bf16, const float* t, const float* mu, const float* gscale, const void* e_store,
-                          const void* xab_bf16, int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end,
-                          float* dz, void* stream);
+int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store,
+                          int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end, float* dz,
+                          void* stream);
 
 #ifdef __cplusplus
 }

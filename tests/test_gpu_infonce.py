@@ -143,7 +143,7 @@ def test_row_range_entry_points_compose(n, d, B, splits, backward_variant):
     assert splits[-1] == R
     gs = torch.ones((), device=DEV)
     loss = torch.zeros((), device=DEV)
-    QW = torch.zeros(A.numel(), device=DEV)
+    QW = torch.zeros(A.numel(), 4, device=DEV)
     from biomedkg_b200.dist import CudaImpl
 
     ranks = [CudaImpl() for _ in splits[1:]]       # one per range, as one per rank: each keeps its own E store for its backward
