@@ -95,13 +95,14 @@ def test_grace_gat_step_trains():
 
     Batch.x, Batch.edge_index = x, ei
     losses = []
-    for _ in range(6):
+    for _ in range(40):
         opt.zero_grad(set_to_none=True)
         loss = mod.training_step(Batch)
         loss.backward()
         opt.step()
         losses.append(float(loss))
-    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    # every step draws new feature / edge / dropout masks, so single losses are noisy: compare windows
+    assert all(l == l for l in losses) and sum(losses[-5:]) < sum(losses[:5]), losses
     assert all(p.grad is not None for p in mod.modality_transform.parameters())   # fuser grads populated, never optimised
 
 
