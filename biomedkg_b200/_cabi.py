@@ -89,10 +89,12 @@ SIGNATURES = {
     "bmkg_infonce_e_store_bytes": (SZ, [I64, I64, I64, I64]),
     "bmkg_infonce_ext": (I, [P, I64, I64, P, P]),
     "bmkg_infonce_fwd": (I, [P, P, P, I64, I, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd": (I, [P, P, P, P, P, I64, I, P, P]),
+    "bmkg_infonce_bwd": (I, [P, P, P, P, P, I64, I, P, P, SZ, P]),
+    "bmkg_infonce_bwd_workspace_bytes": (SZ, [I64, I64, I, I64, I64]),
+    "bmkg_infonce_set_phase_bytes": (I64, [I64]),
     "bmkg_infonce_workspace_bytes_rows": (SZ, [I64, I64, I, I64, I64]),
     "bmkg_infonce_fwd_rows": (I, [P, P, P, I64, I64, I, I64, I64, P, P, P, P, SZ, P]),
-    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, I64, I64, I, I64, I64, P, P]),
+    "bmkg_infonce_bwd_rows": (I, [P, P, P, P, P, I64, I64, I, I64, I64, P, P, SZ, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -100,7 +102,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-if lib.bmkg_abi_version() != 3:
+if lib.bmkg_abi_version() != 4:
     raise ImportError("libbmkg_b200.so ABI version mismatch; rebuild with `python biomedkg_b200/build.py --force`")
 
 #: number of kernel-launching C-ABI calls made so far (bench.py reports it as gpu_launches evidence)

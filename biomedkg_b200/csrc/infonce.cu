@@ -37,6 +37,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/bmkg_b200.h"
@@ -388,37 +390,66 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // backward
 // ----------------------------------------------------------------------------
 // TMEM map: [0,256) dZ accumulator (128 x D fp32), [256,384) S/P buffer 0, [384,512) S/P buffer 1.
-// Column tiles are 128 rows of Z.  MMA1: S[128x128] = Z_U Z_V^T (both operands in smem, K-major).  The two softmax
-// warpgroups turn 64 columns each into bf16 P in place (aliasing their own S columns).  MMA2: dZ[128xD] += P(tmem) * Z_V with
-// the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
+// Column tiles are 128 rows of Z.  MMA1: S[128x128] = Z_U Z_V^T (both operands in smem, K-major).  NCH softmax warpgroups
+// (4 warps each, one per TMEM lane quarter) turn 128/NCH columns each into bf16 P in place: the P of a 32-column group g
+// overwrites the first 16 TMEM columns of that group's own, already consumed, S columns and is published on its own mbarrier,
+// so MMA2 starts on the first K steps while the other groups are still being exponentiated.  MMA2: dZ[128xD] += P(tmem) * Z_V
+// with the SAME smem tile read as an MN-major B operand.  tcgen05.mma ops of one thread execute in issue order, so MMA1(t+2)
 // may be issued into the buffer MMA2(t) still reads without waiting for MMA2(t) to complete.
+// The S -> tcgen05.ld -> ex2 -> tcgen05.st -> P chain is what the tensor pipe waits on (profiles/r2_ncu_infonce_N28000.txt):
+// NCH = 4 puts four softmax warps on every scheduler (32 columns per warp per tile, ~100 registers) so their TMEM / MUFU
+// latencies overlap; NCH = 2 is the earlier shape (64 columns per warp).
+// (Measured and dropped: two independent sets of two warpgroups, one per S/P buffer, so that tile t+1 is exponentiated while
+// tile t is still being published - the sets then share the MUFU pipe and each tile takes twice as long: same period.)
+#ifndef BMKG_BWD_CHUNKS
+#define BMKG_BWD_CHUNKS 4
+#endif
+#ifdef BMKG_BWD_TRACE   // tuning builds only: SM-clock timestamps of CTA 0's first row block (tools/trace_bwd.py)
+__device__ long long g_bwd_trace[64][24];
+#define BWD_TRACE(tile, slot) do { if (blockIdx.x == 0 && first_rb && (tile) < 64) g_bwd_trace[(tile)][(slot)] = clock64(); } while (0)
+#else
+#define BWD_TRACE(tile, slot) do { } while (0)
+#endif
+constexpr int kBwdChunks = BMKG_BWD_CHUNKS;
+static_assert(kBwdChunks == 2 || kBwdChunks == 4, "softmax warpgroups per tile");
+constexpr int kBwdThreads = 64 + 128 * kBwdChunks;   // warp0 TMA, warp1 MMA, then NCH softmax warpgroups
 constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
-constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 2 * kBM * sizeof(float);
+constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 4 * kBM * sizeof(float);
 
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
-infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
+template <int NP, int NCH>
+__global__ void __launch_bounds__(64 + 128 * NCH, 1)
+infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles, int nph, int cph,
                    const float* __restrict__ st /*[>= ntiles*64][8]: (q,q,w,w,t,t,0,0) per row pair, zero padded*/,
                    const float* __restrict__ mu /*[D]*/, const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z,
-                   float* __restrict__ dz) {
+                   float* __restrict__ dz, float* __restrict__ ws_acc /*[nph][nrb*128][D] or null*/,
+                   float* __restrict__ ws_psum /*[nph][nrb*128]*/) {
+  // Work item = (column phase, row block): the column tiles are cut into nph phases of cph tiles and the items are dealt
+  // phase-major, so all CTAs stream the same <= 40 MB of Z at a time (L2-resident when the whole of Z is not) and the last
+  // wave is a fraction of a row block.  With nph > 1 an item leaves its raw partial sums in the workspace and
+  // infonce_bwd_fixup_kernel adds the phases in fixed order; with nph == 1 the epilogue writes dZ itself.
   constexpr int D = NP * kPanelElems;
   constexpr int kPB = kFwdPanelBytes;  // 128 rows x 128 B
+  constexpr int CW = kBN / NCH;        // columns of a tile per softmax warp
+  const int nitems = nrb * nph;
+  constexpr int NSUB = CW / 32;        // 32-column groups per softmax warp
+  constexpr int NWG = NCH;             // softmax warpgroups in the CTA
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kPB * kMaxPanels;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
-  uint64_t* full = bars;                    // [2] V tile landed
-  uint64_t* empty = full + 2;               // [2] V tile no longer needed (MMA2 done)
+  uint64_t* full = bars;                    // [2][4] V tile landed, per 64-feature panel: MMA1 consumes the panels in order, so
+                                            // its first K steps run while the later panels are still in flight
+  uint64_t* empty = full + 8;               // [2] V tile no longer needed (MMA2 done)
   uint64_t* a_full = empty + 2;
   uint64_t* a_empty = a_full + 1;
   uint64_t* s_full = a_empty + 1;           // [2] S ready in TMEM
-  uint64_t* p_full = s_full + 2;            // [2][4] P written back per 32-column quarter (4 warp arrivals each)
+  uint64_t* p_full = s_full + 2;            // [2][4] P written back per 32-column group (4 warp arrivals each)
   uint64_t* dz_full = p_full + 8;
-  uint64_t* dz_empty = dz_full + 1;         // 8 warp arrivals
+  uint64_t* dz_empty = dz_full + 1;         // 4 NWG warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
-  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 warpgroups][128 rows]
+  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [NWG warpgroups][128 rows]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -426,7 +457,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&full[s], 1);
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(&full[s * 4 + q], 1);
       ptx::mbar_init(&empty[s], 1);
       ptx::mbar_init(&s_full[s], 1);
       for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
@@ -434,7 +465,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
     ptx::mbar_init(a_full, 1);
     ptx::mbar_init(a_empty, 1);
     ptx::mbar_init(dz_full, 1);
-    ptx::mbar_init(dz_empty, 8);
+    ptx::mbar_init(dz_empty, 4 * NWG);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmap);
   }
@@ -450,16 +481,20 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
     if (lane == 0) {  // ---------------- TMA producer ----------------
       int stage = 0;
       uint32_t sphase = 0, aphase = 0;
-      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const int ph_i = it / nrb, rb = rb0 + (it - ph_i * nrb);
+        const int ct0 = ph_i * cph, ct1 = min(ct0 + cph, ntiles);
         ptx::mbar_wait(a_empty, aphase ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, tile_bytes);
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
         aphase ^= 1;
-        for (int ct = 0; ct < ntiles; ++ct) {
+        for (int ct = ct0; ct < ct1; ++ct) {
           ptx::mbar_wait(&empty[stage], sphase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], tile_bytes);
           uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
-          for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage], p * kPanelElems, ct * kBN);
+          for (int p = 0; p < npanels; ++p) {
+            ptx::mbar_arrive_expect_tx(&full[stage * 4 + p], kPB);
+            ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage * 4 + p], p * kPanelElems, ct * kBN);
+          }
           if (++stage == kBwdStagesA) { stage = 0; sphase ^= 1; }
         }
       }
@@ -477,23 +512,33 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       }
       uint32_t tcount = 0;  // global tile counter of this CTA: stage = buffer = tcount & 1, phase = (tcount >> 1) & 1
       uint32_t aphase = 0, dzphase = 0;
+      bool first_rb = true;
+      (void)first_rb;
       auto issue_mma1 = [&](uint32_t tc) {
         const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
-        ptx::mbar_wait(&full[b], ph);
-        ptx::tc_fence_after();
+        if (lane == 0) BWD_TRACE(tc, 0);
         const uint32_t d_tmem = tmem_base + kColS + b * 128u;
         const uint64_t bd = bdesc_k[b];
-        if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < NP * 4; ++kk) {
-            const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
-            ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+        for (int p = 0; p < NP; ++p) {
+          ptx::mbar_wait(&full[b * 4 + p], ph);
+          ptx::tc_fence_after();
+          if (p == 0 && lane == 0) BWD_TRACE(tc, 1);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int kk = 4 * p; kk < 4 * p + 4; ++kk) {
+              const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
+              ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+            }
+            if (p == NP - 1) ptx::umma_commit(&s_full[b]);
           }
-          ptx::umma_commit(&s_full[b]);
+          __syncwarp();
         }
-        __syncwarp();
+        if (lane == 0) BWD_TRACE(tc, 2);
       };
-      for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x, first_rb = false) {
+        const int ph_i = it / nrb;
+        const int nt = min(cph, ntiles - ph_i * cph);   // column tiles of this item
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::mbar_wait(dz_empty, dzphase ^ 1);
@@ -505,35 +550,36 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
           const uint64_t bmn = bdesc_mn[b];
           const uint32_t p_tmem = tmem_base + kColS + b * 128u;
           // K = 128 rows of the V tile, 16 per step.  MN-major B: 8-row groups 1024 B apart (SBO), 64-feature panels kPB
-          // apart (LBO).  P of columns [64w, 64w+64) sits (bf16 pairs) in TMEM columns [64w, 64w+32) of the S buffer.
-          // The softmax warpgroups publish P per 32-column quarter (q = 2*chunk + wg), so the first K steps start while
-          // the second chunk is still being exponentiated: quarter q covers columns [64 wg + 32 chunk, +32) = K steps
-          // 4 wg + 2 chunk, +1.
+          // apart (LBO).  P of the 32-column group g sits (bf16 pairs) in TMEM columns [32g, 32g+16) of the S buffer = K steps
+          // 2g, 2g+1.  Groups are waited for in the order they are published (NCH = 2: each warpgroup's first group first).
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            ptx::mbar_wait(&p_full[b * 4 + q], ph);
+          for (int i = 0; i < 4; ++i) {
+            const int g = (NCH == 2) ? ((i & 1) * 2 + (i >> 1)) : i;
+            if (i == 0 && lane == 0) BWD_TRACE(tc, 3);
+            ptx::mbar_wait(&p_full[b * 4 + g], ph);
             ptx::tc_fence_after();
+            if (lane == 0) BWD_TRACE(tc, 4 + i);
             if (ptx::elect_one()) {
-              const int k0 = 4 * (q & 1) + 2 * (q >> 1);
 #pragma unroll
-              for (int k = k0; k < k0 + 2; ++k) {
-                ptx::umma_ts(tmem_base, p_tmem + (uint32_t)(k >> 2) * 64u + (uint32_t)(k & 3) * 8u, bmn + (uint32_t)(k * 2048 >> 4),
-                             idesc2, (!first || q > 0 || k > k0) ? 1u : 0u);
+              for (int k = 2 * g; k < 2 * g + 2; ++k) {
+                ptx::umma_ts(tmem_base, p_tmem + (uint32_t)g * 32u + (uint32_t)(k & 1) * 8u, bmn + (uint32_t)(k * 2048 >> 4),
+                             idesc2, (!first || i > 0 || k > 2 * g) ? 1u : 0u);
               }
-              if (q == 3) ptx::umma_commit(&empty[b]);
+              if (i == 3) ptx::umma_commit(&empty[b]);
             }
             __syncwarp();
           }
+          if (lane == 0) BWD_TRACE(tc, 8);
         };
         issue_mma1(tcount);
-        if (ntiles > 1) issue_mma1(tcount + 1);
-        for (int ct = 0; ct < ntiles; ct += 2) {
+        if (nt > 1) issue_mma1(tcount + 1);
+        for (int ct = 0; ct < nt; ct += 2) {
           issue_mma2(tcount + ct, ct == 0);
-          if (ct + 1 < ntiles) issue_mma2(tcount + ct + 1, false);
-          if (ct + 2 < ntiles) issue_mma1(tcount + ct + 2);
-          if (ct + 3 < ntiles) issue_mma1(tcount + ct + 3);
+          if (ct + 1 < nt) issue_mma2(tcount + ct + 1, false);
+          if (ct + 2 < nt) issue_mma1(tcount + ct + 2);
+          if (ct + 3 < nt) issue_mma1(tcount + ct + 3);
         }
-        tcount += (uint32_t)ntiles;
+        tcount += (uint32_t)nt;
         if (ptx::elect_one()) {
           ptx::umma_commit(dz_full);
           ptx::umma_commit(a_empty);
@@ -543,89 +589,115 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       }
     }
   } else {  // ---------------- softmax / epilogue warpgroups ----------------
-    const int wg = (warp - 2) >> 2;
+    const int wg = (warp - 2) >> 2;          // warpgroup = column chunk of the tile
+    const int wgs = wg;
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
     uint32_t tcount = 0, dzphase = 0;
-    for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
+    bool first_rb = true;
+    (void)first_rb;
+    const int tslot = (warp == 2) ? 9 : (warp == 2 + 4 * (NWG - 1) + 1) ? 15 : -1;   // one warp of the first / last warpgroup
+    (void)tslot;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, first_rb = false) {
+      const int ph_i = it / nrb, rbl = it - ph_i * nrb, rb = rb0 + rbl;
+      const int ct0 = ph_i * cph, ct1 = min(ct0 + cph, ntiles);
       const int row = rb * kBM + lrow;
       // S = d_u . d_v here (no ext K step: in this kernel the extra MMA costs more than the packed ALU it saves, measured);
       // the rank-1 terms enter through  P_uv = 2^S (q_u w_v + q_v w_u),  q = t w,  w = 2^a
       const float* su = st + (size_t)(row >> 1) * 8 + (row & 1);
-      const float qu = __ldg(su), wu = __ldg(su + 2), tu = __ldg(su + 4);   // zeros for padding rows
+      const float qu = __ldg(su), wu = __ldg(su + 2);   // zeros for padding rows
       const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
-      const int colbase = wg * 64;
-      float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warpgroup's columns (before the bf16 rounding)
-      for (int ct = 0; ct < ntiles; ++ct, ++tcount) {
-        // every tile is split between the two warpgroups (64 columns each)
+      const int colbase = wg * CW;
+      float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warp's columns (before the bf16 rounding)
+      for (int ct = ct0; ct < ct1; ++ct, ++tcount) {
+        // every tile is split between the NCH warpgroups (CW columns each)
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        const float4* cvp = reinterpret_cast<const float4*>(st + (size_t)gcol0 * 4);   // (q, q, w, w) of a column pair every 8 floats
-        float4 cvr[16];  // first 32 columns: fetched before the wait so the load latency is off the S -> P chain
+        // (q, q, w, w) of a column pair every 8 floats; lane-uniform, L1-resident.  Fetched 8 columns ahead of their use (the
+        // first 8 before the wait), so the load latency is off the S -> P chain without holding a whole group in registers.
+        const float4* cvp = reinterpret_cast<const float4*>(st + (size_t)gcol0 * 4);
+        float4 cv[2][4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 2 * q);
+        for (int q = 0; q < 4; ++q) cv[0][q] = __ldg(cvp + 2 * q);
+        if (tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot);
         ptx::mbar_wait(&s_full[b], ph);
         ptx::tc_fence_after();
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld32(taddr, r0);
-        ptx::tmem_ld32(taddr + 32, r1);
-        ptx::tmem_ld_wait();
-        const bool diag = (row >= gcol0) && (row < gcol0 + 64);
-        auto make_p = [&](const uint32_t (&r)[32], int c, uint32_t (&pk)[16]) {
+        if (tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot + 1);
+        const bool diag = (row >= gcol0) && (row < gcol0 + CW);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 c01 = cvr[2 * q], c23 = cvr[2 * q + 1];
-            // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
-            const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
-            const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
-            float2 p01 = __fmul2_rn(ex2_pair(r[4 * q + 0], r[4 * q + 1], BMKG_POLY_BWD >= 2), t01);
-            float2 p23 = __fmul2_rn(ex2_pair(r[4 * q + 2], r[4 * q + 3], BMKG_POLY_BWD >= 1), t23);
-            if (diag) {
-              const int j = gcol0 + c * 32 + 4 * q;
-              if (j + 0 == row) p01.x = 0.f;
-              if (j + 1 == row) p01.y = 0.f;
-              if (j + 2 == row) p23.x = 0.f;
-              if (j + 3 == row) p23.y = 0.f;
+        for (int j = 0; j < NSUB; ++j) {
+          uint32_t r[32], pk[16];
+          ptx::tmem_ld32(taddr + 32 * j, r);
+          ptx::tmem_ld_wait();
+          if (j == 0 && tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot + 2);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {          // 8 columns per step
+            const int gi = 4 * j + o;            // 8-column step within this warp's CW columns
+            if (gi + 1 < 4 * NSUB) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) cv[(gi + 1) & 1][q] = __ldg(cvp + 8 * (gi + 1) + 2 * q);
             }
-            psum = __fadd2_rn(psum, __fadd2_rn(p01, p23));
-            pk[2 * q] = pack2(p01.x, p01.y);
-            pk[2 * q + 1] = pack2(p23.x, p23.y);
-          }
-        };
-        uint32_t pk[16];
-        make_p(r0, 0, pk);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) cvr[q] = __ldg(cvp + 32 + 2 * q);   // second 32 columns (L1-resident, lane-uniform)
-        ptx::tmem_st16(taddr, pk);  // P (bf16 pairs) aliases this warpgroup's own, already consumed, S columns
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + wg]);        // quarter 0/1: first 32 columns of this warpgroup
-        make_p(r1, 1, pk);
-        ptx::tmem_st16(taddr + 16, pk);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + 2 + wg]);    // quarter 2/3: second 32 columns
+            for (int h = 0; h < 2; ++h) {
+              const float4 c01 = cv[gi & 1][2 * h], c23 = cv[gi & 1][2 * h + 1];
+              const int e = 8 * o + 4 * h;       // element within the 32-column group
+              // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
+              const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
+              const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
+              float2 p01 = __fmul2_rn(ex2_pair(r[e + 0], r[e + 1], BMKG_POLY_BWD >= 2), t01);
+              float2 p23 = __fmul2_rn(ex2_pair(r[e + 2], r[e + 3], BMKG_POLY_BWD >= 1), t23);
+              if (diag) {
+                const int jc = gcol0 + 32 * j + e;
+                if (jc + 0 == row) p01.x = 0.f;
+                if (jc + 1 == row) p01.y = 0.f;
+                if (jc + 2 == row) p23.x = 0.f;
+                if (jc + 3 == row) p23.y = 0.f;
+              }
+              psum = __fadd2_rn(psum, __fadd2_rn(p01, p23));
+              pk[e / 2] = pack2(p01.x, p01.y);
+              pk[e / 2 + 1] = pack2(p23.x, p23.y);
+            }
+          }
+          if (j == 0 && tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot + 3);
+          ptx::tmem_st16(taddr + 32 * j, pk);  // P (bf16 pairs) aliases this group's own, already consumed, S columns
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_full[b * 4 + wg * NSUB + j]);
+          if (tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot + 4 + (j == NSUB - 1 ? 1 : 0));
+        }
       }
-      // epilogue: dZ rows of this block.  wg0 -> columns [0,D/2), wg1 -> [D/2,D).  Both need the row sum of P over ALL
-      // columns: exchange the two warpgroups' halves through shared memory (the next row block cannot overwrite s_rowsum
+      // epilogue: dZ rows of this block, 32-column chunks dealt round-robin to the warpgroups.  All need the row sum of P over
+      // ALL columns: exchange the warpgroups' parts through shared memory (the next row block cannot overwrite s_rowsum
       // before every softmax warp has arrived on dz_empty, i.e. after its read below).
-      s_rowsum[wg * kBM + lrow] = psum.x + psum.y;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float prow = (s_rowsum[lrow] + s_rowsum[kBM + lrow]) - 2.0f;   // all-zero columns have q_v = w_v = 0: they added nothing
-      (void)tu;
+      s_rowsum[wgs * kBM + lrow] = psum.x + psum.y;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NWG) : "memory");
+      float prow = 0.f;     // all-zero columns have q_v = w_v = 0: they added nothing
+#pragma unroll
+      for (int g = 0; g < NWG; ++g) prow += s_rowsum[g * kBM + lrow];
       ptx::mbar_wait(dz_full, dzphase);
       dzphase ^= 1;
       ptx::tc_fence_after();
-      const int half = D / 2;
       const int blk = row / B;
       const int pair = (blk & 1) ? row - B : row + B;
       const bool valid = (blk >> 1) * B + (row - blk * B) < N;
-      for (int c0 = wg * half; c0 < (wg + 1) * half; c0 += 32) {
+      if (ws_acc != nullptr) {   // one of several column phases: raw partial sums, added up by infonce_bwd_fixup_kernel
+        const size_t wrow = ((size_t)ph_i * nrb + rbl) * kBM + lrow;
+        if (wgs == 0) ws_psum[wrow] = prow;
+        for (int c0 = wgs * 32; c0 < D; c0 += NWG * 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          uint4* out = reinterpret_cast<uint4*>(ws_acc + wrow * D + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) out[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+      }
+      prow -= 2.0f;
+      for (int c0 = wgs * 32; ws_acc == nullptr && c0 < D; c0 += NWG * 32) {
         uint32_t r[32];
         ptx::tmem_ld32(lane_base + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
@@ -660,6 +732,43 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// Column phases of the backward -> dZ:  dZ_u = ln2/2N [ sum_phases (sum_v P_uv d_v) + mu (sum_phases sum_v P_uv - 2) - 2 d_pair ],
+// phases added in index order (deterministic).  One thread per 4 features, D/4 threads per row.
+__global__ void __launch_bounds__(256) infonce_bwd_fixup_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_psum, int nph,
+                                                               int rb0, int nrb, int N, int B, int D, const float* __restrict__ mu,
+                                                               const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z,
+                                                               float* __restrict__ dz) {
+  const int tpr = D / 4;                                   // threads per row
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int lrow_all = (int)(tid / tpr);
+  const int c = (int)(tid % tpr) * 4;
+  if (lrow_all >= nrb * kBM) return;
+  const int row = rb0 * kBM + lrow_all;
+  const int blk = row / B;
+  if ((blk >> 1) * B + (row - blk * B) >= N) return;       // layout padding
+  const int pair = (blk & 1) ? row - B : row + B;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ps = 0.f;
+  for (int p = 0; p < nph; ++p) {
+    const size_t wrow = (size_t)p * nrb * kBM + lrow_all;
+    const float4 v = *reinterpret_cast<const float4*>(ws_acc + wrow * D + c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    ps += ws_psum[wrow];
+  }
+  ps -= 2.0f;
+  const float gcoef = gscale[0] * 0.6931471805599453f / (2.0f * (float)N);
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mu + c));
+  const uint2 zr = __ldg(reinterpret_cast<const uint2*>(z + (size_t)pair * D + c));
+  const float2 z01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zr.x));
+  const float2 z23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zr.y));
+  float4 o;
+  o.x = gcoef * (fmaf(m.x, ps, acc.x) - 2.f * z01.x);
+  o.y = gcoef * (fmaf(m.y, ps, acc.y) - 2.f * z01.y);
+  o.z = gcoef * (fmaf(m.z, ps, acc.z) - 2.f * z23.x);
+  o.w = gcoef * (fmaf(m.w, ps, acc.w) - 2.f * z23.y);
+  *reinterpret_cast<float4*>(dz + (size_t)row * D + c) = o;
 }
 
 // ----------------------------------------------------------------------------
@@ -1110,8 +1219,39 @@ int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, i
   return bmkg_infonce_fwd_rows(z_bf16, a, xab_bf16, N, N, D, 0, 2 * N, loss, state, e_store, ws, ws_bytes, stream);
 }
 
+// Column phases of the recompute backward for a launch of nrb row blocks over ntiles column tiles: at least as many as keep one
+// phase's slice of Z (cph tiles x 128 rows x D bf16) within ~40 MB of L2, then the count (of the next few) whose items
+// (row block, phase) fill the SMs' waves best; 4 tiles of fill / drain / epilogue are charged per item.  1 = no phases.
+static int64_t g_phase_bytes = (int64_t)40 << 20;
+static void bwd_phases(int nrb, int ntiles, int D, int* nph, int* cph) {
+  const int64_t cmax = std::max<int64_t>(1, g_phase_bytes / ((int64_t)kBN * D * 2));
+  const int lo = (int)ceil_div(ntiles, cmax);
+  int64_t best_cost = -1;
+  for (int n = lo; n <= lo + 7 && n <= ntiles; ++n) {
+    const int c = (int)ceil_div(ntiles, n), ne = (int)ceil_div(ntiles, c);
+    const int64_t cost = ceil_div((int64_t)nrb * ne, kNumSMs) * (c + 4);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; *nph = ne; *cph = c; }
+  }
+}
+
+int64_t bmkg_infonce_set_phase_bytes(int64_t bytes) {
+  const int64_t old = g_phase_bytes;
+  if (bytes > 0) g_phase_bytes = bytes;
+  return old;
+}
+
+size_t bmkg_infonce_bwd_workspace_bytes(int64_t N, int64_t B, int D, int64_t row_begin, int64_t row_end) {
+  if (!block_ok(N, B) || D < 64 || D > 256 || D % 64 != 0) return 0;
+  const int64_t rows = stacked_rows(N, B);
+  if (!rows_range_ok(rows, row_begin, row_end)) return 0;
+  const int nrb = (int)ceil_div(row_end - row_begin, kBM), ntiles = (int)ceil_div(rows, kBN);
+  int nph = 1, cph = ntiles;
+  bwd_phases(nrb, ntiles, D, &nph, &cph);
+  return nph > 1 ? (size_t)nph * nrb * kBM * (D + 1) * sizeof(float) : 0;
+}
+
 int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store, int64_t N,
-                          int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* stream) {
+                          int64_t B, int D, int64_t row_begin, int64_t row_end, float* dz, void* ws, size_t ws_bytes, void* stream) {
   const float* qw = state;
   BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
@@ -1124,7 +1264,7 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* m
   CUtensorMap tmap;
   int rc = make_z_tensormap(&tmap, z_bf16, rows, D, kBN);
   if (rc != BMKG_OK) return rc;
-  const int grid = nrb < kNumSMs ? nrb : kNumSMs;
+  int grid = nrb < kNumSMs ? nrb : kNumSMs;
   const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(z_bf16);
   const float* qwp = qw;
   if (e_store) {   // the forward kept E = 2^S for this row range: stream it back instead of recomputing S
@@ -1146,8 +1286,22 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* m
   }
 #define BMKG_LAUNCH_BWD(NP_)                                                                                        \
   {                                                                                                                 \
-    if (!set_smem(infonce_bwd_kernel<NP_>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                                 \
-    infonce_bwd_kernel<NP_><<<grid, kThreads, kBwdSmemBytesA, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, qwp, mu, gscale, zp, dz); \
+    if (!set_smem(infonce_bwd_kernel<NP_, kBwdChunks>, kBwdSmemBytesA)) return BMKG_ERR_LAUNCH;                     \
+    infonce_bwd_kernel<NP_, kBwdChunks><<<grid, kBwdThreads, kBwdSmemBytesA, st>>>(tmap, (int)N, (int)B, rb0, nrb, ntiles, nph, cph, qwp, mu, \
+                                                                                   gscale, zp, dz, ws_acc, ws_psum);                  \
+  }
+  // column phases need the workspace of bmkg_infonce_bwd_workspace_bytes; without it the launch runs as one phase (correct, slower)
+  int nph = 1, cph = ntiles;
+  bwd_phases(nrb, ntiles, D, &nph, &cph);
+  float *ws_acc = nullptr, *ws_psum = nullptr;
+  if (nph > 1 && ws != nullptr && ws_bytes >= (size_t)nph * nrb * kBM * (D + 1) * sizeof(float)) {
+    BMKG_REQUIRE(aligned16(ws), BMKG_ERR_MISALIGNED);
+    ws_acc = static_cast<float*>(ws);
+    ws_psum = ws_acc + (size_t)nph * nrb * kBM * D;
+    grid = (int)std::min<int64_t>((int64_t)nrb * nph, kNumSMs);
+  } else {
+    nph = 1;
+    cph = ntiles;
   }
   switch (D / kPanelElems) {
     case 1: BMKG_LAUNCH_BWD(1) break;
@@ -1157,12 +1311,23 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* m
   }
 #undef BMKG_LAUNCH_BWD
   BMKG_CHECK_LAUNCH();
+  if (ws_acc != nullptr) {
+    const int64_t threads = (int64_t)nrb * kBM * (D / 4);
+    infonce_bwd_fixup_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(ws_acc, ws_psum, nph, rb0, nrb, (int)N, (int)B, D, mu, gscale, zp, dz);
+    BMKG_CHECK_LAUNCH();
+  }
   return BMKG_OK;
 }
 
 int bmkg_infonce_bwd(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store, int64_t N, int D,
-                     float* dz, void* stream) {
-  return bmkg_infonce_bwd_rows(z_bf16, state, mu, gscale, e_store, N, N, D, 0, 2 * N, dz, stream);
+                     float* dz, void* ws, size_t ws_bytes, void* stream) {
+  return bmkg_infonce_bwd_rows(z_bf16, state, mu, gscale, e_store, N, N, D, 0, 2 * N, dz, ws, ws_bytes, stream);
 }
 
 }  // extern "C"
+
+#ifdef BMKG_BWD_TRACE
+extern "C" int bmkg_debug_bwd_trace(long long* out /*[64*24]*/) {
+  return cudaMemcpyFromSymbol(out, bmkg::nce::g_bwd_trace, sizeof(long long) * 64 * 24) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -794,7 +794,8 @@ class _InfoNCEFn(torch.autograd.Function):
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _stream())
+        ws = _ws(lib.bmkg_infonce_bwd_workspace_bytes(N, N, D, 0, 2 * N), h1.device) if e_store is None else None
+        call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _p(ws), 0 if ws is None else ws.numel(), _stream())
         release_e_store(e_store)
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
         call("bmkg_l2norm_scale_bwd", _p(h1), _p(inv_norm), _p(dz), N, D, ctx.scale, _p(dh1), _stream())

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BMKG_ABI_VERSION 3
+#define BMKG_ABI_VERSION 4
 
 int bmkg_abi_version(void);
 /* last CUresult (or 100000 + cudaError*100 + query status) seen while building a TMA tensor map; 0 = none */
@@ -260,8 +260,15 @@ size_t bmkg_infonce_workspace_bytes(int64_t num_nodes, int dim);
 int bmkg_infonce_ext(const float* a, int64_t num_nodes, int64_t view_block, void* xab_bf16, void* stream);
 int bmkg_infonce_fwd(const void* z_bf16, const float* a, const void* xab_bf16, int64_t num_nodes, int dim, float* loss, float* state,
                      void* e_store, void* ws, size_t ws_bytes, void* stream);
+/* bwd workspace (0 = none needed): when the stacked matrix does not fit L2, or the row blocks leave most of a wave idle, the
+ * recompute backward walks the columns in phases and adds the phases' partial sums in a fixed order
+ * (infonce_bwd_fixup_kernel); ws may be NULL - the launch then runs as one phase (same result up to fp32 summation order). */
+size_t bmkg_infonce_bwd_workspace_bytes(int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end);
+/* tuning: bytes of Z one column phase may span (default 40 MB, sized for the L2 of one B200 die); returns the previous value,
+ * bytes <= 0 only queries.  Process-wide; changes the sizes bmkg_infonce_bwd_workspace_bytes reports. */
+int64_t bmkg_infonce_set_phase_bytes(int64_t bytes);
 int bmkg_infonce_bwd(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store,
-                     int64_t num_nodes, int dim, float* dz, void* stream);
+                     int64_t num_nodes, int dim, float* dz, void* ws, size_t ws_bytes, void* stream);
 /* Row-range variants: only rows [row_begin, row_end) of the stacked matrix are processed against ALL columns.
  * row_begin % 128 == 0; row_end % 128 == 0 or row_end == R.  fwd_rows writes this range's share of the loss (the shares of
  * all ranges add up to the loss) and state for the range; bwd_rows needs state for all rows (all-gathered) and writes dz rows of
@@ -273,7 +280,7 @@ int bmkg_infonce_fwd_rows(const void* z_bf16, const float* a, const void* xab_bf
                           void* stream);
 int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* mu, const float* gscale, const void* e_store,
                           int64_t num_nodes, int64_t view_block, int dim, int64_t row_begin, int64_t row_end, float* dz,
-                          void* stream);
+                          void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def test_python_binding_covers_header(libpath):
     from biomedkg_b200 import _cabi
 
     assert sorted(_cabi.SIGNATURES) == _declared()
-    assert _cabi.lib.bmkg_abi_version() == 3
+    assert _cabi.lib.bmkg_abi_version() == 4
     assert b"workspace" in _cabi.lib.bmkg_error_string(-3)
 
 

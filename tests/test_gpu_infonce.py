@@ -126,11 +126,14 @@ def _stacked_operand(h1, h2, B, tau=0.2):
 
 @pytest.mark.parametrize("n,d,B,splits", [(1000, 256, 1000, (0, 768, 2000)), (300, 64, 128, (0, 256, 512, 768)),
                                           (4096, 256, 1024, (0, 2048, 4096, 8192)), (1000, 256, 384, (0, 768, 1536, 2304))])
-def test_row_range_entry_points_compose(n, d, B, splits, backward_variant):
+@pytest.mark.parametrize("phase_kb", [None, 96], ids=["one_phase", "phases"])
+def test_row_range_entry_points_compose(n, d, B, splits, backward_variant, phase_kb):
     """bmkg_infonce_{fwd,bwd}_rows over disjoint row ranges of the block-interleaved layout (what each rank of the row-sharded
     multi-GPU path runs; B = that path's node block, with zero padding rows when B does not divide N) add up to the
-    single-launch result of the plain [h1; h2] layout: loss shares sum to the loss, every node's gradient is identical."""
+    single-launch result of the plain [h1; h2] layout: loss shares sum to the loss, every node's gradient is identical.
+    'phases': the same with the recompute backward forced to walk the columns in several phases (as it does at cfg4 size)."""
     from biomedkg_b200 import ops
+    from biomedkg_b200._cabi import lib
 
     g = torch.Generator().manual_seed(n)
     h1 = torch.randn(n, d, generator=g).to(DEV)
@@ -153,7 +156,13 @@ def test_row_range_entry_points_compose(n, d, B, splits, backward_variant):
         QW[r0:r1] = qw[r0:r1]
         assert (impl_r.e_store is not None) == (backward_variant == "stored_e")
     assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref)), (float(loss), float(ref))
-    dz = torch.cat([impl_r.bwd_rows(Z, QW, mu, gs, n, B, r0, r1)[: r1 - r0] for impl_r, r0, r1 in zip(ranks, splits, splits[1:])])
+    old = lib.bmkg_infonce_set_phase_bytes(phase_kb * 1024 if phase_kb else 0)
+    try:
+        if phase_kb and backward_variant == "recompute":
+            assert lib.bmkg_infonce_bwd_workspace_bytes(n, B, d, splits[0], splits[1]) > 0
+        dz = torch.cat([impl_r.bwd_rows(Z, QW, mu, gs, n, B, r0, r1)[: r1 - r0] for impl_r, r0, r1 in zip(ranks, splits, splits[1:])])
+    finally:
+        lib.bmkg_infonce_set_phase_bytes(old)
     dz = dz.view(-1, 2, B, d)                                                  # [block, view, row, D]
     dz1 = dz[:, 0].reshape(-1, d)[:n].contiguous()
     dz2 = dz[:, 1].reshape(-1, d)[:n].contiguous()
@@ -264,3 +273,38 @@ def test_infonce_cluster_closed_form_large_n(n):
         # bf16 rounding of its one large component (up to 2^-9 of 2.7) shifts a whole block of similarities coherently
         # (up to 0.03 in log2 units = 2 % of 2^S) instead of averaging out as it does for generic rows
         assert rel_err(got, gref) < 3e-2
+
+
+@pytest.mark.parametrize("n,d,phase_kb", [(3000, 256, 512), (1100, 64, 64), (5000, 192, 2048), (700, 128, None)])
+def test_infonce_backward_column_phases_match_single_phase(n, d, phase_kb):
+    """The recompute backward walks the columns in phases (L2-sized slices of Z; also used to fill the SMs when there are fewer
+    row blocks than SMs) and infonce_bwd_fixup_kernel adds the phases' partial sums in fixed order.  Against the same launch
+    WITHOUT a workspace (= one phase, the epilogue writes dZ itself): equal up to fp32 summation order; bitwise reproducible."""
+    from biomedkg_b200 import ops
+    from biomedkg_b200._cabi import lib
+    from biomedkg_b200.ops import _p, _stream, _ws, call
+
+    g = torch.Generator().manual_seed(n + d)
+    h1 = torch.randn(n, d, generator=g).to(DEV)
+    h2 = (h1 + 0.7 * torch.randn(n, d, generator=g).to(DEV))
+    impl, Z, A, mu, _, _ = _stacked_operand(h1, h2, n)
+    _, state = impl.fwd_rows(Z, A, n, n, 0, 2 * n)
+    gs = torch.ones((), device=DEV)
+
+    def bwd(ws):
+        dz = torch.zeros(2 * n, d, device=DEV)
+        call("bmkg_infonce_bwd", _p(Z), _p(state), _p(mu), _p(gs), None, n, d, _p(dz), _p(ws), 0 if ws is None else ws.numel(), _stream())
+        return dz
+
+    one = bwd(None)
+    old = lib.bmkg_infonce_set_phase_bytes(phase_kb * 1024 if phase_kb else 0)
+    try:
+        nbytes = int(lib.bmkg_infonce_bwd_workspace_bytes(n, n, d, 0, 2 * n))
+        assert nbytes > 0                                   # (fewer row blocks than SMs: phases by default, too)
+        pa, pb = bwd(_ws(nbytes, DEV)), bwd(_ws(nbytes, DEV))
+        small = bwd(_ws(nbytes // 2, DEV))                  # a workspace that is too small falls back to one phase
+    finally:
+        lib.bmkg_infonce_set_phase_bytes(old)
+    assert torch.equal(pa, pb)
+    assert torch.equal(small, one)
+    assert rel_err(pa, one) < 2e-5, rel_err(pa, one)
