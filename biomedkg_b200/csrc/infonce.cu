@@ -399,11 +399,16 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 // The S -> tcgen05.ld -> ex2 -> tcgen05.st -> P chain is what the tensor pipe waits on (profiles/r2_ncu_infonce_N28000.txt):
 // NCH = 4 puts four softmax warps on every scheduler (32 columns per warp per tile, ~100 registers) so their TMEM / MUFU
 // latencies overlap; NCH = 2 is the earlier shape (64 columns per warp).
-// (Measured and dropped: two independent sets of two warpgroups, one per S/P buffer, so that tile t+1 is exponentiated while
-// tile t is still being published - the sets then share the MUFU pipe and each tile takes twice as long: same period.)
+// (Measured and dropped, before and after the issue-order change below: two independent sets of two warpgroups, one per S/P
+// buffer, so that tile t+1 is exponentiated while tile t is still being published - the sets then share the MUFU pipe and each
+// tile takes twice as long: 57.4 vs 50.4 ms at N=130k.)
 #ifndef BMKG_BWD_CHUNKS
 #define BMKG_BWD_CHUNKS 4
 #endif
+#ifndef BMKG_BWD_ORDER
+#define BMKG_BWD_ORDER 1
+#endif
+
 #ifdef BMKG_BWD_TRACE   // tuning builds only: SM-clock timestamps of CTA 0's first row block (tools/trace_bwd.py)
 __device__ long long g_bwd_trace[64][24];
 #define BWD_TRACE(tile, slot) do { if (blockIdx.x == 0 && first_rb && (tile) < 64) g_bwd_trace[(tile)][(slot)] = clock64(); } while (0)
@@ -441,8 +446,9 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
   uint64_t* full = bars;                    // [2][4] V tile landed, per 64-feature panel: MMA1 consumes the panels in order, so
                                             // its first K steps run while the later panels are still in flight
-  uint64_t* empty = full + 8;               // [2] V tile no longer needed (MMA2 done)
-  uint64_t* a_full = empty + 2;
+  uint64_t* empty = full + 8;               // [2][4] V tile panel no longer needed: MMA2 runs panel by panel (N = 64), so the
+                                            // reload of the first panels overlaps the rest of MMA2 instead of idling the tensor pipe
+  uint64_t* a_full = empty + 8;
   uint64_t* a_empty = a_full + 1;
   uint64_t* s_full = a_empty + 1;           // [2] S ready in TMEM
   uint64_t* p_full = s_full + 2;            // [2][4] P written back per 32-column group (4 warp arrivals each)
@@ -458,7 +464,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       for (int q = 0; q < 4; ++q) ptx::mbar_init(&full[s * 4 + q], 1);
-      ptx::mbar_init(&empty[s], 1);
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(&empty[s * 4 + q], 1);
       ptx::mbar_init(&s_full[s], 1);
       for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
     }
@@ -489,9 +495,9 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
         aphase ^= 1;
         for (int ct = ct0; ct < ct1; ++ct) {
-          ptx::mbar_wait(&empty[stage], sphase ^ 1);
           uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
           for (int p = 0; p < npanels; ++p) {
+            ptx::mbar_wait(&empty[stage * 4 + p], sphase ^ 1);
             ptx::mbar_arrive_expect_tx(&full[stage * 4 + p], kPB);
             ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage * 4 + p], p * kPanelElems, ct * kBN);
           }
@@ -502,7 +508,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   } else if (warp == 1) {
     {  // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues) ----------------
       constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T   (A, B K-major in smem)
-      constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, D, 0, 1);    // dZ += P Z_V     (A tmem, B MN-major)
+      constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, kPanelElems, 0, 1);   // dZ[:, panel] += P Z_V[:, panel]  (A tmem, B MN-major)
       const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA), 16, 1024);
       uint64_t bdesc_k[2], bdesc_mn[2];  // per stage: K-major view (MMA1) and MN-major view (MMA2) of the same tile
       for (int sg = 0; sg < 2; ++sg) {
@@ -542,43 +548,58 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         ptx::mbar_wait(a_full, aphase);
         aphase ^= 1;
         ptx::mbar_wait(dz_empty, dzphase ^ 1);
-        // Issue order MMA1(t) MMA1(t+1) | MMA2(t) MMA2(t+1) MMA1(t+2) MMA1(t+3) | ...: with two smem stages and two S/P
-        // buffers this puts one full MMA (1024 tensor cycles) between "stage freed by MMA2(t)" and "MMA1(t+2) needs the
-        // reloaded stage", and between "S(t) ready" and "MMA2(t) needs P(t)", instead of exposing those latencies.
+        // Issue order MMA1(t) MMA1(t+1) | MMA2(t) MMA1(t+2) | MMA2(t+1) MMA1(t+3) | ...: S(t+2) is produced as early as the S/P
+        // buffer allows (right behind MMA2(t)), so the softmax warps never wait for it; the shared-memory stage MMA1(t+2)
+        // needs is the one MMA2(t) reads, which is why MMA2 releases it panel by panel (the reload of panel 0 is under way
+        // while panels 1-3 are still being multiplied) and MMA1 consumes it panel by panel.  (BMKG_BWD_ORDER=0: the earlier
+        // pairwise order MMA2(t) MMA2(t+1) MMA1(t+2) MMA1(t+3).)
         auto issue_mma2 = [&](uint32_t tc, bool first) {
           const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
           const uint64_t bmn = bdesc_mn[b];
           const uint32_t p_tmem = tmem_base + kColS + b * 128u;
-          // K = 128 rows of the V tile, 16 per step.  MN-major B: 8-row groups 1024 B apart (SBO), 64-feature panels kPB
-          // apart (LBO).  P of the 32-column group g sits (bf16 pairs) in TMEM columns [32g, 32g+16) of the S buffer = K steps
-          // 2g, 2g+1.  Groups are waited for in the order they are published (NCH = 2: each warpgroup's first group first).
+          // K = 128 rows of the V tile, 16 per step; one 64-feature panel (N = 64) at a time, so each panel of the stage is
+          // released as soon as its 8 K steps are issued-and-done.  MN-major B: 8-row groups 1024 B apart (SBO).  P of the
+          // 32-column group g sits (bf16 pairs) in TMEM columns [32g, 32g+16) of the S buffer = K steps 2g, 2g+1; the first
+          // panel waits for the groups as it goes (they are published in order), the others find them ready.
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int g = (NCH == 2) ? ((i & 1) * 2 + (i >> 1)) : i;
-            if (i == 0 && lane == 0) BWD_TRACE(tc, 3);
-            ptx::mbar_wait(&p_full[b * 4 + g], ph);
-            ptx::tc_fence_after();
-            if (lane == 0) BWD_TRACE(tc, 4 + i);
-            if (ptx::elect_one()) {
+          for (int p = 0; p < NP; ++p) {
 #pragma unroll
-              for (int k = 2 * g; k < 2 * g + 2; ++k) {
-                ptx::umma_ts(tmem_base, p_tmem + (uint32_t)g * 32u + (uint32_t)(k & 1) * 8u, bmn + (uint32_t)(k * 2048 >> 4),
-                             idesc2, (!first || i > 0 || k > 2 * g) ? 1u : 0u);
+            for (int i = 0; i < 4; ++i) {
+              const int g = (NCH == 2) ? ((i & 1) * 2 + (i >> 1)) : i;
+              if (p == 0) {
+                if (i == 0 && lane == 0) BWD_TRACE(tc, 3);
+                ptx::mbar_wait(&p_full[b * 4 + g], ph);
+                ptx::tc_fence_after();
+                if (lane == 0) BWD_TRACE(tc, 4 + i);
               }
-              if (i == 3) ptx::umma_commit(&empty[b]);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 2 * g; k < 2 * g + 2; ++k) {
+                  ptx::umma_ts(tmem_base + (uint32_t)(p * kPanelElems), p_tmem + (uint32_t)g * 32u + (uint32_t)(k & 1) * 8u,
+                               bmn + (uint32_t)((p * kPB + k * 2048) >> 4), idesc2, (!first || i > 0 || k > 2 * g) ? 1u : 0u);
+                }
+                if (i == 3) ptx::umma_commit(&empty[b * 4 + p]);
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
           if (lane == 0) BWD_TRACE(tc, 8);
         };
         issue_mma1(tcount);
         if (nt > 1) issue_mma1(tcount + 1);
+#if BMKG_BWD_ORDER == 0
         for (int ct = 0; ct < nt; ct += 2) {
           issue_mma2(tcount + ct, ct == 0);
           if (ct + 1 < nt) issue_mma2(tcount + ct + 1, false);
           if (ct + 2 < nt) issue_mma1(tcount + ct + 2);
           if (ct + 3 < nt) issue_mma1(tcount + ct + 3);
         }
+#else
+        for (int ct = 0; ct < nt; ++ct) {
+          issue_mma2(tcount + ct, ct == 0);
+          if (ct + 2 < nt) issue_mma1(tcount + ct + 2);
+        }
+#endif
         tcount += (uint32_t)nt;
         if (ptx::elect_one()) {
           ptx::umma_commit(dz_full);
