@@ -30,8 +30,10 @@
 // accumulators; two softmax warpgroups pull tiles with tcgen05.ld, apply ex2, mask the diagonal and keep per-row
 // partial sums in registers.  Work items are ordered chunk-major, and when Z is larger than L2 the chunks are sized to
 // fit it, so all CTAs sweep the same L2-resident column chunk at the same time.  Backward: same stream;
-// P = 2^S (1/R_u + 1/R_v) is written back to TMEM as bf16 (aliasing S) and a second tcgen05.mma with A from TMEM and
-// the same smem tile as an MN-major B accumulates dZ_u = sum_v P_uv z_v in TMEM.
+// P = 2^S (1/R_u + 1/R_v) is written back to TMEM as bf16 (aliasing S) by four softmax warpgroups and a second tcgen05.mma
+// with A from TMEM and the same smem tile as an MN-major B accumulates dZ_u = sum_v P_uv z_v in TMEM, one 64-feature panel
+// at a time so that the shared-memory stage is released (and reloaded) panel by panel; work items are (column phase, row
+// block) - L2-sized column slices, whole waves - with a fixed-order fix-up kernel when there is more than one phase.
 //
 // Tensor-bound.  Algorithmic FLOPs: fwd 6 N^2 D, bwd 8 N^2 D.
 #include <cuda.h>
