@@ -45,6 +45,22 @@ def test_host_side_size_queries(libpath):
     assert lib.bmkg_edge_sort_workspace_bytes(1000, 50_000) >= 50_000 * 24
     assert lib.bmkg_csr_filter_workspace_bytes(1000, 50_000) >= 50_000 * 8
     assert lib.bmkg_infonce_workspace_bytes(8000, 256) > 0
+    # column phases of the InfoNCE backward (host-side schedule): cfg4 on one GPU = 2032 row blocks x 4 phases, a rank of the
+    # 8-GPU row-sharded run = 254 row blocks x 4 phases (7 whole waves of 148 items instead of 1.7 waves of row blocks);
+    # N = 28k already fills 2.96 waves with one phase; the phase budget is a process-wide tuning knob
+    n4 = 130_000
+    assert lib.bmkg_infonce_bwd_workspace_bytes(n4, n4, 256, 0, 2 * n4) == 4 * 2032 * 128 * 257 * 4
+    blk = 16_256                                                        # dist.shard_layout(130000, 8): ceil(N/8) rounded up to 128
+    assert lib.bmkg_infonce_stacked_rows(n4, blk) == 2 * 8 * blk
+    assert lib.bmkg_infonce_bwd_workspace_bytes(n4, blk, 256, 0, 2 * blk) == 4 * 254 * 128 * 257 * 4
+    assert lib.bmkg_infonce_bwd_workspace_bytes(28_000, 28_000, 256, 0, 56_000) == 0
+    assert lib.bmkg_infonce_bwd_workspace_bytes(n4, n4, 257, 0, 2 * n4) == 0           # unsupported width: nothing to size
+    old = lib.bmkg_infonce_set_phase_bytes(1 << 20)
+    try:
+        assert old == 40 << 20 and lib.bmkg_infonce_set_phase_bytes(0) == 1 << 20    # <= 0 only queries
+        assert lib.bmkg_infonce_bwd_workspace_bytes(28_000, 28_000, 256, 0, 56_000) > 0
+    finally:
+        lib.bmkg_infonce_set_phase_bytes(old)
 
 
 def test_module_surface_matches_reference(libpath):
