@@ -420,8 +420,16 @@ __device__ long long g_bwd_trace[64][24];
 constexpr int kBwdChunks = BMKG_BWD_CHUNKS;
 static_assert(kBwdChunks == 2 || kBwdChunks == 4, "softmax warpgroups per tile");
 constexpr int kBwdThreads = 64 + 128 * kBwdChunks;   // warp0 TMA, warp1 MMA, then NCH softmax warpgroups
-constexpr int kBwdStagesA = 2;  // V-tile stages (64 KB each) next to the 64 KB stationary block
-constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * kMaxPanels * (1 + kBwdStagesA) + 256 + 4 * kBM * sizeof(float);
+// Column tiles live in a ring of 16 KB panel slots (128 rows x 64 features) next to the 64 KB stationary block: MMA1 and MMA2 both
+// work panel by panel, so a tile's panels need not be adjacent, and 9 slots (two tiles + one spare) let the first panel of tile
+// t+2 land before MMA2(t) has released anything - with 8 the tensor pipe idled ~260 clocks per tile waiting for it.
+#ifndef BMKG_BWD_SLOTS
+#define BMKG_BWD_SLOTS 9
+#endif
+constexpr int kBwdSlots = BMKG_BWD_SLOTS;   // 8 = two whole tiles (the earlier two-stage behaviour), 9 = one spare panel
+static_assert(kBwdSlots >= 8 && kBwdSlots <= 9, "panel ring size (shared memory: 64 KB + slots x 16 KB)");
+constexpr int kBwdBarBytes = 512;
+constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * (kMaxPanels + kBwdSlots) + kBwdBarBytes + 4 * kBM * sizeof(float);
 
 template <int NP, int NCH>
 __global__ void __launch_bounds__(64 + 128 * NCH, 1)
@@ -445,28 +453,30 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kPB * kMaxPanels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * kMaxPanels * (1 + kBwdStagesA));
-  uint64_t* full = bars;                    // [2][4] V tile landed, per 64-feature panel: MMA1 consumes the panels in order, so
-                                            // its first K steps run while the later panels are still in flight
-  uint64_t* empty = full + 8;               // [2][4] V tile panel no longer needed: MMA2 runs panel by panel (N = 64), so the
-                                            // reload of the first panels overlaps the rest of MMA2 instead of idling the tensor pipe
-  uint64_t* a_full = empty + 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPB * (kMaxPanels + kBwdSlots));
+  uint64_t* full = bars;                    // [slots] panel landed: MMA1 consumes a tile's panels in order, so its first K steps
+                                            // run while the later panels are still in flight
+  uint64_t* empty = full + kBwdSlots;       // [slots] panel no longer needed: MMA2 runs panel by panel (N = 64), so the reload
+                                            // of the first panels overlaps the rest of MMA2 instead of idling the tensor pipe
+  uint64_t* a_full = empty + kBwdSlots;
   uint64_t* a_empty = a_full + 1;
   uint64_t* s_full = a_empty + 1;           // [2] S ready in TMEM
   uint64_t* p_full = s_full + 2;            // [2][4] P written back per 32-column group (4 warp arrivals each)
   uint64_t* dz_full = p_full + 8;
   uint64_t* dz_empty = dz_full + 1;         // 4 NWG warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 1);
-  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [NWG warpgroups][128 rows]
+  float* s_rowsum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBwdBarBytes);   // [NWG warpgroups][128 rows]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   constexpr int npanels = NP;
 
   if (threadIdx.x == 0) {
+    for (int q = 0; q < kBwdSlots; ++q) {
+      ptx::mbar_init(&full[q], 1);
+      ptx::mbar_init(&empty[q], 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      for (int q = 0; q < 4; ++q) ptx::mbar_init(&full[s * 4 + q], 1);
-      for (int q = 0; q < 4; ++q) ptx::mbar_init(&empty[s * 4 + q], 1);
       ptx::mbar_init(&s_full[s], 1);
       for (int q = 0; q < 4; ++q) ptx::mbar_init(&p_full[s * 4 + q], 4);
     }
@@ -487,7 +497,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer ----------------
-      int stage = 0;
+      int slot = 0;
       uint32_t sphase = 0, aphase = 0;
       for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const int ph_i = it / nrb, rb = rb0 + (it - ph_i * nrb);
@@ -497,13 +507,12 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         for (int p = 0; p < npanels; ++p) ptx::tma_load_2d(sA + p * kPB, &tmap, a_full, p * kPanelElems, rb * kBM);
         aphase ^= 1;
         for (int ct = ct0; ct < ct1; ++ct) {
-          uint8_t* dst = sB + (size_t)stage * kPB * kMaxPanels;
           for (int p = 0; p < npanels; ++p) {
-            ptx::mbar_wait(&empty[stage * 4 + p], sphase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full[stage * 4 + p], kPB);
-            ptx::tma_load_2d(dst + p * kPB, &tmap, &full[stage * 4 + p], p * kPanelElems, ct * kBN);
+            ptx::mbar_wait(&empty[slot], sphase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[slot], kPB);
+            ptx::tma_load_2d(sB + (size_t)slot * kPB, &tmap, &full[slot], p * kPanelElems, ct * kBN);
+            if (++slot == kBwdSlots) { slot = 0; sphase ^= 1; }
           }
-          if (++stage == kBwdStagesA) { stage = 0; sphase ^= 1; }
         }
       }
     }
@@ -512,12 +521,10 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       constexpr uint32_t idesc1 = ptx::idesc_bf16_f32(kBM, kBN, 0, 0);  // S = Z_U Z_V^T   (A, B K-major in smem)
       constexpr uint32_t idesc2 = ptx::idesc_bf16_f32(kBM, kPanelElems, 0, 1);   // dZ[:, panel] += P Z_V[:, panel]  (A tmem, B MN-major)
       const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA), 16, 1024);
-      uint64_t bdesc_k[2], bdesc_mn[2];  // per stage: K-major view (MMA1) and MN-major view (MMA2) of the same tile
-      for (int sg = 0; sg < 2; ++sg) {
-        const uint32_t a = ptx::smem_u32(sB + (size_t)sg * kPB * kMaxPanels);
-        bdesc_k[sg] = ptx::smem_desc_sw128(a, 16, 1024);
-        bdesc_mn[sg] = ptx::smem_desc_sw128(a, kPB, 1024);
-      }
+      // slot 0 of the panel ring: K-major view (MMA1) and MN-major view (MMA2); slot s is (s * kPB) >> 4 further in the
+      // descriptor's address field.  Panel p of the CTA's tile tc sits in slot (NP tc + p) mod kBwdSlots, use (NP tc + p) / kBwdSlots.
+      const uint64_t bdesc_k0 = ptx::smem_desc_sw128(ptx::smem_u32(sB), 16, 1024);
+      const uint64_t bdesc_mn0 = ptx::smem_desc_sw128(ptx::smem_u32(sB), kPB, 1024);
       uint32_t tcount = 0;  // global tile counter of this CTA: stage = buffer = tcount & 1, phase = (tcount >> 1) & 1
       uint32_t aphase = 0, dzphase = 0;
       bool first_rb = true;
@@ -526,17 +533,18 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
         if (lane == 0) BWD_TRACE(tc, 0);
         const uint32_t d_tmem = tmem_base + kColS + b * 128u;
-        const uint64_t bd = bdesc_k[b];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          ptx::mbar_wait(&full[b * 4 + p], ph);
+          const uint32_t gp = tc * (uint32_t)NP + (uint32_t)p, use = gp / (uint32_t)kBwdSlots, slot = gp - use * (uint32_t)kBwdSlots;
+          ptx::mbar_wait(&full[slot], use & 1u);
           ptx::tc_fence_after();
           if (p == 0 && lane == 0) BWD_TRACE(tc, 1);
+          const uint64_t bd = bdesc_k0 + (uint64_t)(slot * (uint32_t)(kPB >> 4));
           if (ptx::elect_one()) {
 #pragma unroll
             for (int kk = 4 * p; kk < 4 * p + 4; ++kk) {
-              const uint32_t off16 = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
-              ptx::umma_ss(d_tmem, adesc + off16, bd + off16, idesc1, kk > 0 ? 1u : 0u);
+              const uint32_t offa = (uint32_t)(((kk >> 2) * kPB + (kk & 3) * 32) >> 4);
+              ptx::umma_ss(d_tmem, adesc + offa, bd + (uint32_t)(((kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
             }
             if (p == NP - 1) ptx::umma_commit(&s_full[b]);
           }
@@ -557,7 +565,6 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         // pairwise order MMA2(t) MMA2(t+1) MMA1(t+2) MMA1(t+3).)
         auto issue_mma2 = [&](uint32_t tc, bool first) {
           const uint32_t b = tc & 1u, ph = (tc >> 1) & 1u;
-          const uint64_t bmn = bdesc_mn[b];
           const uint32_t p_tmem = tmem_base + kColS + b * 128u;
           // K = 128 rows of the V tile, 16 per step; one 64-feature panel (N = 64) at a time, so each panel of the stage is
           // released as soon as its 8 K steps are issued-and-done.  MN-major B: 8-row groups 1024 B apart (SBO).  P of the
@@ -565,6 +572,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
           // panel waits for the groups as it goes (they are published in order), the others find them ready.
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
+            const uint32_t gp = tc * (uint32_t)NP + (uint32_t)p, use = gp / (uint32_t)kBwdSlots, slot = gp - use * (uint32_t)kBwdSlots;
+            const uint64_t bmn = bdesc_mn0 + (uint64_t)(slot * (uint32_t)(kPB >> 4));
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int g = (NCH == 2) ? ((i & 1) * 2 + (i >> 1)) : i;
@@ -578,9 +587,9 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
 #pragma unroll
                 for (int k = 2 * g; k < 2 * g + 2; ++k) {
                   ptx::umma_ts(tmem_base + (uint32_t)(p * kPanelElems), p_tmem + (uint32_t)g * 32u + (uint32_t)(k & 1) * 8u,
-                               bmn + (uint32_t)((p * kPB + k * 2048) >> 4), idesc2, (!first || i > 0 || k > 2 * g) ? 1u : 0u);
+                               bmn + (uint32_t)((k * 2048) >> 4), idesc2, (!first || i > 0 || k > 2 * g) ? 1u : 0u);
                 }
-                if (i == 3) ptx::umma_commit(&empty[b * 4 + p]);
+                if (i == 3) ptx::umma_commit(&empty[slot]);
               }
               __syncwarp();
             }
