@@ -340,13 +340,14 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
     float R = 0.f;
     for (int s = 0; s < nslots; ++s) R += partial[(size_t)s * rows_padded + u];
     R -= npad;                      // all-zero columns (layout padding, TMA out-of-range fill) have S'' = 0 and contributed exactly 1.0 each
-    // forward -> backward state, per PAIR of rows (q, q, w, w, t, t, 0, 0): t = 1/R'', w = 2^a, q = t w, so that
-    // P_uv = 2^(S''_uv) (t_u + t_v) = 2^(d_u.d_v) (q_u w_v + q_v w_u); packed so the backward's fp32x2 math loads register pairs
+    // forward -> backward state, per FOUR rows (q0..q3, w0..w3, t0..t3, 0, 0, 0, 0): t = 1/R'', w = 2^a, q = t w, so that
+    // P_uv = 2^(S''_uv) (t_u + t_v) = 2^(d_u.d_v) (q_u w_v + q_v w_u); the backward fetches (q, w) of four columns with one
+    // 256-bit request and its fp32x2 math takes them as register pairs
     const float tv = 1.0f / R, wv = exp2f(a[u]);
-    float* sp = st + (size_t)(u >> 1) * 8 + (u & 1);
+    float* sp = st + (size_t)(u >> 2) * 16 + (u & 3);
     sp[0] = tv * wv;
-    sp[2] = wv;
-    sp[4] = tv;
+    sp[4] = wv;
+    sp[8] = tv;
     term = logf(R);
     if ((blk & 1) == 0) {   // view-1 row: positive pair with the same node's view-2 row
       const uint4* za = reinterpret_cast<const uint4*>(z + (size_t)u * D);
@@ -362,15 +363,12 @@ __global__ void __launch_bounds__(256) infonce_finalize_rows_kernel(const float*
       term -= 2.0f * 0.6931471805599453f * (dot + a[u] + a[u + B]);
     }
   } else if (u < rows_pad_end) {
-    float* sp = st + (size_t)(u >> 1) * 8 + (u & 1);
+    float* sp = st + (size_t)(u >> 2) * 16 + (u & 3);
     sp[0] = 0.f;
-    sp[2] = 0.f;
     sp[4] = 0.f;
+    sp[8] = 0.f;
   }
-  if (u < rows_pad_end && (u & 1) == 0) {   // the two unused floats of the pair
-    st[(size_t)(u >> 1) * 8 + 6] = 0.f;
-    st[(size_t)(u >> 1) * 8 + 7] = 0.f;
-  }
+  if (u < rows_pad_end) st[(size_t)(u >> 2) * 16 + 12 + (u & 3)] = 0.f;   // the unused quarter of the record
   term = warp_sum(term);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
   __syncthreads();
@@ -411,6 +409,16 @@ __global__ void infonce_finalize_loss_kernel(const float* __restrict__ block_par
 #define BMKG_BWD_ORDER 1
 #endif
 
+// (q, w) of four consecutive columns = the first 32 bytes of a 64-byte state record, fetched with ONE 256-bit request
+struct ColVec4 { float q0, q1, q2, q3, w0, w1, w2, w3; };
+__device__ __forceinline__ ColVec4 ldg_colvec4(const float* p) {
+  ColVec4 v;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v.q0), "=f"(v.q1), "=f"(v.q2), "=f"(v.q3), "=f"(v.w0), "=f"(v.w1), "=f"(v.w2), "=f"(v.w3)
+               : "l"(p));
+  return v;
+}
+
 #ifdef BMKG_BWD_TRACE   // tuning builds only: SM-clock timestamps of CTA 0's first row block (tools/trace_bwd.py)
 __device__ long long g_bwd_trace[64][24];
 #define BWD_TRACE(tile, slot) do { if (blockIdx.x == 0 && first_rb && (tile) < 64) g_bwd_trace[(tile)][(slot)] = clock64(); } while (0)
@@ -434,7 +442,7 @@ constexpr size_t kBwdSmemBytesA = 1024 + (size_t)kFwdPanelBytes * (kMaxPanels + 
 template <int NP, int NCH>
 __global__ void __launch_bounds__(64 + 128 * NCH, 1)
 infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles, int nph, int cph,
-                   const float* __restrict__ st /*[>= ntiles*64][8]: (q,q,w,w,t,t,0,0) per row pair, zero padded*/,
+                   const float* __restrict__ st /*[>= ntiles*32][16]: (q0..3, w0..3, t0..3, 0 x 4) per four rows, zero padded*/,
                    const float* __restrict__ mu /*[D]*/, const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z,
                    float* __restrict__ dz, float* __restrict__ ws_acc /*[nph][nrb*128][D] or null*/,
                    float* __restrict__ ws_psum /*[nph][nrb*128]*/) {
@@ -638,8 +646,8 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
       const int row = rb * kBM + lrow;
       // S = d_u . d_v here (no ext K step: in this kernel the extra MMA costs more than the packed ALU it saves, measured);
       // the rank-1 terms enter through  P_uv = 2^S (q_u w_v + q_v w_u),  q = t w,  w = 2^a
-      const float* su = st + (size_t)(row >> 1) * 8 + (row & 1);
-      const float qu = __ldg(su), wu = __ldg(su + 2);   // zeros for padding rows
+      const float* su = st + (size_t)(row >> 2) * 16 + (row & 3);
+      const float qu = __ldg(su), wu = __ldg(su + 4);   // zeros for padding rows
       const float2 qu2 = make_float2(qu, qu), wu2 = make_float2(wu, wu);
       const int colbase = wg * CW;
       float2 psum = make_float2(0.f, 0.f);     // fp32 row sum of P over this warp's columns (before the bf16 rounding)
@@ -648,12 +656,14 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;  // global column (row of Z) of the first element
-        // (q, q, w, w) of a column pair every 8 floats; lane-uniform, L1-resident.  Fetched 8 columns ahead of their use (the
-        // first 8 before the wait), so the load latency is off the S -> P chain without holding a whole group in registers.
-        const float4* cvp = reinterpret_cast<const float4*>(st + (size_t)gcol0 * 4);
-        float4 cv[2][4];
+        // (q0..q3, w0..w3) of four columns every 16 floats; lane-uniform, L1-resident, one 256-bit request per four columns (the
+        // L1 / shared-memory port these share with the MMA operand reads is the busiest unit of the kernel).  Fetched 8 columns
+        // ahead of their use (the first 8 before the wait), so the load latency is off the S -> P chain without holding a
+        // whole group in registers.
+        const float* cvp = st + (size_t)gcol0 * 4;
+        ColVec4 cv[2][2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cv[0][q] = __ldg(cvp + 2 * q);
+        for (int q = 0; q < 2; ++q) cv[0][q] = ldg_colvec4(cvp + 16 * q);
         if (tslot >= 0 && lane == 0) BWD_TRACE(tcount, tslot);
         ptx::mbar_wait(&s_full[b], ph);
         ptx::tc_fence_after();
@@ -670,15 +680,15 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int r
             const int gi = 4 * j + o;            // 8-column step within this warp's CW columns
             if (gi + 1 < 4 * NSUB) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) cv[(gi + 1) & 1][q] = __ldg(cvp + 8 * (gi + 1) + 2 * q);
+              for (int q = 0; q < 2; ++q) cv[(gi + 1) & 1][q] = ldg_colvec4(cvp + 32 * (gi + 1) + 16 * q);
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const float4 c01 = cv[gi & 1][2 * h], c23 = cv[gi & 1][2 * h + 1];
+              const ColVec4 c = cv[gi & 1][h];
               const int e = 8 * o + 4 * h;       // element within the 32-column group
               // packed fp32x2: t = q_u w_v + q_v w_u, p = 2^S t for two columns per instruction
-              const float2 t01 = __ffma2_rn(qu2, make_float2(c01.z, c01.w), __fmul2_rn(make_float2(c01.x, c01.y), wu2));
-              const float2 t23 = __ffma2_rn(qu2, make_float2(c23.z, c23.w), __fmul2_rn(make_float2(c23.x, c23.y), wu2));
+              const float2 t01 = __ffma2_rn(qu2, make_float2(c.w0, c.w1), __fmul2_rn(make_float2(c.q0, c.q1), wu2));
+              const float2 t23 = __ffma2_rn(qu2, make_float2(c.w2, c.w3), __fmul2_rn(make_float2(c.q2, c.q3), wu2));
               float2 p01 = __fmul2_rn(ex2_pair(r[e + 0], r[e + 1], BMKG_POLY_BWD >= 2), t01);
               float2 p23 = __fmul2_rn(ex2_pair(r[e + 2], r[e + 3], BMKG_POLY_BWD >= 1), t23);
               if (diag) {
@@ -820,7 +830,7 @@ constexpr size_t kBwdESmemBytes = 1024 + 2 * (size_t)kFwdPanelBytes * kMaxPanels
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int rb0, int nrb, int ntiles,
-                     const float* __restrict__ st /*(q,q,w,w,t,t,0,0) per row pair*/, const float* __restrict__ mu,
+                     const float* __restrict__ st /*(q0..3, w0..3, t0..3, 0 x 4) per four rows*/, const float* __restrict__ mu,
                      const float* __restrict__ gscale, const __nv_bfloat16* __restrict__ z, const uint8_t* __restrict__ e_store,
                      float* __restrict__ dz) {
   constexpr int D = NP * kPanelElems;
@@ -933,7 +943,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
     uint32_t tcount = 0, dzphase = 0, es = 0, eph = 0;
     for (int rb = rb0 + blockIdx.x; rb < rb0 + nrb; rb += gridDim.x) {
       const int row = rb * kBM + lrow;
-      const float tu = __ldg(st + (size_t)(row >> 1) * 8 + 4 + (row & 1));          // 1/R''_u; zero for padding rows
+      const float tu = __ldg(st + (size_t)(row >> 2) * 16 + 8 + (row & 3));         // 1/R''_u; zero for padding rows
       const float2 tu2 = make_float2(tu, tu);
       const int colbase = wg * 64;
       float2 psum = make_float2(0.f, 0.f);
@@ -941,10 +951,10 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmap, int N, int B, int
         const uint32_t b = tcount & 1u, ph = (tcount >> 1) & 1u;
         const uint32_t taddr = lane_base + kColS + b * 128u + (uint32_t)colbase;
         const int gcol0 = ct * kBN + colbase;
-        const float* cvp = st + (size_t)gcol0 * 4 + 4;    // (t, t) of a column pair every 8 floats
+        const float* cvp = st + (size_t)gcol0 * 4 + 8;    // (t0..t3) of four columns every 16 floats
         float2 cvr[32];   // 1/R'' of this warpgroup's 64 columns
 #pragma unroll
-        for (int q = 0; q < 32; ++q) cvr[q] = __ldg(reinterpret_cast<const float2*>(cvp + 8 * q));
+        for (int q = 0; q < 32; ++q) cvr[q] = __ldg(reinterpret_cast<const float2*>(cvp + 16 * (q >> 1) + 2 * (q & 1)));
         ptx::mbar_wait(&e_full[es], eph);
         // this thread's row, columns [64 wg, 64 wg + 64): 16-byte chunks 8 wg .. 8 wg + 7 of the chunk-major tile
         const uint4* ep = reinterpret_cast<const uint4*>(sE + (size_t)es * kETileBytes + (size_t)(wg * 8) * 2048 + (size_t)lrow * 16);
@@ -1287,7 +1297,8 @@ int bmkg_infonce_bwd_rows(const void* z_bf16, const float* state, const float* m
   const float* qw = state;
   BMKG_REQUIRE(z_bf16 && qw && mu && gscale && dz && block_ok(N, B), BMKG_ERR_BAD_ARG);
   BMKG_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, BMKG_ERR_UNSUPPORTED);
-  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && aligned16(qw) && aligned16(mu) && aligned16(e_store), BMKG_ERR_MISALIGNED);
+  BMKG_REQUIRE(aligned16(z_bf16) && aligned16(dz) && (reinterpret_cast<uintptr_t>(qw) & 31) == 0 && aligned16(mu) && aligned16(e_store),
+               BMKG_ERR_MISALIGNED);   // state: 256-bit loads
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t rows = stacked_rows(N, B);
   BMKG_REQUIRE(rows_range_ok(rows, row_begin, row_end), BMKG_ERR_BAD_ARG);

@@ -780,7 +780,7 @@ class _InfoNCEFn(torch.autograd.Function):
              a.data_ptr() + N * 4, _stream())
         call("bmkg_infonce_ext", _p(a), N, N, _p(xab), _stream())
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        t = torch.empty(rp, 4, dtype=torch.float32, device=dev)      # forward -> backward state: (q, q, w, w, t, t, 0, 0) per row pair
+        t = torch.empty(rp, 4, dtype=torch.float32, device=dev)      # forward -> backward state: (q0..q3, w0..w3, t0..t3, 0 x 4) per four rows
         ws = _ws(lib.bmkg_infonce_workspace_bytes(N, D), dev)
         e_store = alloc_e_store(N, N, 0, 2 * N, dev) if any(ctx.needs_input_grad[:2]) else None      # only a backward reads it
         call("bmkg_infonce_fwd", _p(z), _p(a), _p(xab), N, D, _p(loss), _p(t), _p(e_store), _p(ws), ws.numel(), _stream())

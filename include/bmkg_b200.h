@@ -244,8 +244,9 @@ int bmkg_linear_tn(const void* g_bf16, const void* x_bf16, const float* addend, 
  *   R = bmkg_infonce_stacked_rows(N, B) = 2 B ceil(N/B); rows of nodes >= N are ZERO in z and a; P = bmkg_infonce_padded_rows(N, B)
  *   (R rounded up to 128) and a is zero beyond R.  With B = the node block of one rank, a rank's rows of both views are ONE
  *   contiguous, 128-aligned range - the unit of the row-sharded multi-GPU path.
- * fwd writes the scalar loss and state fp32 [P][4], an opaque hand-over to bwd: per pair of rows (q, q, w, w, t, t, 0, 0) with
- * t_u = 1 / R''_u, R''_u = sum_{v != u} 2^(d_u.d_v + a_u + a_v), w = 2^a, q = t w (zeros for padding rows);
+ * fwd writes the scalar loss and state fp32 [P][4] (32-byte aligned), an opaque hand-over to bwd: per four rows
+ * (q0..q3, w0..w3, t0..t3, 0, 0, 0, 0) with t_u = 1 / R''_u, R''_u = sum_{v != u} 2^(d_u.d_v + a_u + a_v), w = 2^a, q = t w
+ * (zeros for padding rows); rows [r0, r1) with r0, r1 multiples of 4 occupy floats [4 r0, 4 r1);
  * bwd writes dL/dz fp32 [R, D] (valid rows only) scaled by *gscale:
  *   dZ_u = gscale ln2/2N [ sum_v P_uv d_v + mu (sum_v P_uv - 2) - 2 d_pair(u) ],
  *   P_uv = 2^(d_u.d_v + a_u + a_v) (t_u + t_v) = 2^(d_u.d_v) (q_u w_v + q_v w_u).
