@@ -58,8 +58,11 @@ def synth(cfg, seed, pin=False):
         ei = torch.stack([torch.randint(0, N, (E,), generator=g, dtype=torch.int64), dst])
     else:
         ei = torch.randint(0, N, (2, E), generator=g, dtype=torch.int64)
-    if pin:
-        x, ei = x.pin_memory(), ei.pin_memory()
+    if pin:   # pinned on the NUMA node local to this rank's GPU when the topology is known (biomedkg_b200/hostmem.py)
+        from biomedkg_b200.hostmem import pinned_near
+
+        d = torch.cuda.current_device()
+        x, ei = pinned_near(x, d), pinned_near(ei, d)
     return x, ei
 
 
@@ -519,13 +522,14 @@ def run_ours(args, rank, world, local_rank):
     x_src, ei_src = x_host, ei_host
     if full_shard:   # a sharded loader: every rank reads its node block of the features and 1/world of the edge list from the host
         from biomedkg_b200.dist import edge_chunk, gather_edge_index, shard_layout
+        from biomedkg_b200.hostmem import pinned_near
 
         b0, b1 = shard_layout(N, world)[1][rank]
-        x_src = x_host[b0:b1].contiguous().pin_memory()
+        x_src = pinned_near(x_host[b0:b1].contiguous(), torch.cuda.current_device())
         per, c0, c1 = edge_chunk(E, world, rank)
         ei_src = torch.zeros(2, per, dtype=torch.int64)
         ei_src[:, : c1 - c0] = ei_host[:, c0:c1]
-        ei_src = ei_src.pin_memory()
+        ei_src = pinned_near(ei_src, torch.cuda.current_device())
 
     # Two device staging buffers, as a loader keeps them: the copy of step k+1 lands in the buffer step k-1 used (its
     # "consumed" event is waited for on the copy stream), so the timed loop allocates nothing - with a fresh 1.2 GB tensor per

@@ -241,13 +241,18 @@ def sorted_graph(edge_index: torch.Tensor, num_nodes: int, cache: bool = True) -
         return SortedGraph(edge_index, num_nodes, assume_hubs=edge_index.size(1) > HUB_THRESHOLD)
     if not cache:
         return SortedGraph(edge_index, num_nodes)
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), edge_index.device)
-    sg = _GRAPH_CACHE.get(key)
-    if sg is None:
-        if len(_GRAPH_CACHE) >= 8:
-            _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
-        sg = SortedGraph(edge_index, num_nodes)
-        _GRAPH_CACHE[key] = sg
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), int(num_nodes), edge_index.device)
+    hit = _GRAPH_CACHE.get(key)
+    if hit is not None and hit[0] == edge_index._version:
+        return hit[1]
+    # new contents in the same buffer (a loader's staging tensor): drop the stale sort BEFORE sorting again, so its arrays go
+    # back to the allocator and are reused - keeping one entry per version made every step of a streaming loop cudaMalloc
+    _GRAPH_CACHE.pop(key, None)
+    del hit
+    if len(_GRAPH_CACHE) >= 8:
+        _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
+    sg = SortedGraph(edge_index, num_nodes)
+    _GRAPH_CACHE[key] = (edge_index._version, sg)
     return sg
 
 
