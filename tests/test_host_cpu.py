@@ -110,3 +110,16 @@ def test_sampler_structure_checker_accepts_oracle_and_rejects_corruptions():
             assert osamp.check_structure(ei, n, seeds, fan, n_id, sub[:, :-1], eid[:-1])      # a missing edge breaks the fan-out count
             sw = n_id.copy(); sw[[len(seeds), len(n_id) - 1]] = sw[[len(n_id) - 1, len(seeds)]]
             assert osamp.check_structure(ei, n, seeds, fan, sw, sub, eid)                      # wrong node order
+
+
+def test_hostmem_placement_hint_degrades_quietly():
+    """biomedkg_b200.hostmem: without a GPU / NVML there is no placement hint - gpu_local_cpus answers None instead of raising
+    (pinned_near then pins wherever the thread runs), and the calling thread's CPU affinity is left as it was."""
+    import os
+
+    from biomedkg_b200.hostmem import gpu_local_cpus
+
+    before = os.sched_getaffinity(0)
+    cpus = gpu_local_cpus(0)
+    assert cpus is None or (isinstance(cpus, set) and cpus <= before)
+    assert os.sched_getaffinity(0) == before
