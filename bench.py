@@ -638,9 +638,12 @@ def run_ours(args, rank, world, local_rank):
             for fn in ("r2_traffic.json", "r1_traffic.json"):
                 path = os.path.join(ROOT, "profiles", fn)
                 if os.path.exists(path):
-                    tj = json.load(open(path))["infonce_bwd_kernel"]
-                    if tj["N"] == N:
-                        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    allj = json.load(open(path))
+                    for tj in (allj.get(f"infonce_bwd_kernel_N{N}"), allj.get("infonce_bwd_kernel")):
+                        if tj and tj.get("N") == N and world == 1:     # a capture of the full-range launch at this size
+                            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+                            break
+                    if traffic is not None:
                         break
         except Exception:  # noqa: BLE001
             pass
