@@ -91,7 +91,7 @@ class CudaImpl:
 
     def bwd_rows(self, Z, T, mu, g, N, B, r0, r1):
         """-> dZ fp32 [r1 - r0, D] of this range (the kernel addresses dz by global row: pass the buffer shifted by -r0 rows)"""
-        from .ops import _p, _stream, _ws, call, lib, release_e_store
+        from .ops import _p, _stream, _ws_optional, call, lib, release_e_store
 
         D = Z.size(1)
         if T.size(0) < int(lib.bmkg_infonce_padded_rows(N, B)):
@@ -99,7 +99,7 @@ class CudaImpl:
         dz = torch.zeros(max(r1 - r0, 1), D, dtype=torch.float32, device=Z.device)
         if r1 > r0:
             e_store = getattr(self, "e_store", None)
-            ws = _ws(lib.bmkg_infonce_bwd_workspace_bytes(N, B, D, r0, r1), Z.device) if e_store is None else None
+            ws = _ws_optional(lib.bmkg_infonce_bwd_workspace_bytes(N, B, D, r0, r1), Z.device) if e_store is None else None
             call("bmkg_infonce_bwd_rows", _p(Z), _p(T), _p(mu), _p(g), _p(e_store), N, B, D, r0, r1,
                  dz.data_ptr() - r0 * D * 4, _p(ws), 0 if ws is None else ws.numel(), _stream())
             release_e_store(getattr(self, "e_store", None))

@@ -42,6 +42,17 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def _ws_optional(nbytes: int, device):
+    """Workspace that only buys speed (the entry point accepts NULL and takes its slower single-pass route): None when there is
+    nothing to allocate or the allocation does not fit (the column phases of a 1 M-node InfoNCE backward want ~50 GB)."""
+    if int(nbytes) <= 0:
+        return None
+    try:
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    except torch.cuda.OutOfMemoryError:
+        return None
+
+
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """bf16 x bf16 -> fp32 (fp32 accumulate, no bf16 rounding of the result) - library GEMM, only for shapes the tcgen05
     kernels do not take (``gemm_nt`` / ``gemm_tn`` below)."""
@@ -799,7 +810,7 @@ class _InfoNCEFn(torch.autograd.Function):
         N, D = h1.shape
         g = g.contiguous().float()
         dz = torch.empty(2 * N, D, dtype=torch.float32, device=h1.device)
-        ws = _ws(lib.bmkg_infonce_bwd_workspace_bytes(N, N, D, 0, 2 * N), h1.device) if e_store is None else None
+        ws = _ws_optional(lib.bmkg_infonce_bwd_workspace_bytes(N, N, D, 0, 2 * N), h1.device) if e_store is None else None
         call("bmkg_infonce_bwd", _p(z), _p(t), _p(mu), _p(g), _p(e_store), N, D, _p(dz), _p(ws), 0 if ws is None else ws.numel(), _stream())
         release_e_store(e_store)
         dh1, dh2 = torch.empty_like(h1), torch.empty_like(h2)
